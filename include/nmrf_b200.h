@@ -1,0 +1,180 @@
+/*
+ * nmrf_b200.h -- C-ABI of libnmrf_b200.so: the NMRF-Stereo inference hot path on B200 (sm_100a).
+ *
+ * Drop-in boundary for aeolusguan/NMRF (paths below are relative to that repository).
+ * Every entry point
+ *   - takes plain device pointers + sizes + a CUDA stream (passed as void*, = cudaStream_t),
+ *   - never allocates, frees or synchronises (safe to capture in a CUDA graph),
+ *   - returns 0 on success, non-zero NMRF_ERR_* otherwise; nmrf_last_error() gives the text.
+ * All tensors are fp32 unless noted, contiguous, 16-byte aligned.  Feature maps are NHWC
+ * (torch channels_last); token tensors are [rows, 128] row-major, row = ((b*H + y)*W + x)*K + n,
+ * exactly the reference's '(b h w) n c' order (nmrf/models/NMP.py:347,360).
+ *
+ * Packed weights: the reference's nn.Linear weights ([out,in] row-major) are used as they are,
+ * except that the input dimension is zero-padded to a multiple of 16 and q/k/v projections
+ * that share an input are stacked along `out` (see nmrf_b200/plan.py, which does the packing
+ * with torch ops at load time; layouts are documented per struct below).
+ */
+#ifndef NMRF_B200_H
+#define NMRF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMRF_B200_ABI_VERSION 1
+
+enum {
+  NMRF_OK = 0,
+  NMRF_ERR_BAD_ARG = 1,      /* null pointer / unsupported dimension */
+  NMRF_ERR_UNSUPPORTED = 2,  /* valid in the reference but outside this build's limits */
+  NMRF_ERR_CUDA = 3          /* cudaGetLastError() != cudaSuccess after a launch */
+};
+
+/* ---- library helpers ------------------------------------------------------------------- */
+int nmrf_abi_version(void);
+const char* nmrf_last_error(void);          /* thread-local, valid until the next call */
+/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+uint64_t nmrf_launch_count(void);
+
+/* ---- generic fused token GEMM -------------------------------------------------------------
+ * Y[r, n] = act( sum_k A[r,k] * W[n,k] + bias[n] ) (+ R[r,n])
+ * A[r, :] = concat( LN?(X[r, 0:Kx]), E[r / ediv, 0:Ke] ),   W is [N, ldw] with ldw >= Kx+Ke.
+ * This is the dense part of every nn.Linear on the path (NMP.py:82,84,326,332,337,522,525,537,
+ * 607-612,675; NMRF.py:82-83,105; DPN.py:65) with LayerNorm (eps 1e-5), concat, bias, ReLU/GELU
+ * and the residual add fused in.  Kx, Ke, ldw, ldx, lde, ldy, ldr must be multiples of 4.
+ */
+typedef struct {
+  const float* X; int ldx; int Kx;
+  const float* E; int lde; int Ke; int ediv;   /* E may be NULL (Ke = 0) */
+  const float* ln_gamma; const float* ln_beta; /* both NULL = no LayerNorm; else Kx must be 128 */
+  const float* W; int ldw;
+  const float* bias;                           /* [N] or NULL */
+  const float* R; int ldr;                     /* residual or NULL; may alias Y */
+  float* Y; int ldy;
+  int rows; int N;
+  int act;                                     /* 0 none, 1 ReLU, 2 GELU (erf) */
+} nmrf_gemm_args;
+int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
+
+/* ---- A1+A2: cost volume + seed extraction ------------------------------------------------
+ * replaces build_correlation_volume (nmrf/models/submodule.py:4-23) and DPN.forward step 1
+ * (nmrf/models/DPN.py:115-125): conv1d 4->8->16->1 (k5,pad2)+ReLU, softmax over D, 1-D NMS
+ * (max_pool1d k3), suppressed := eps, top-K.
+ * Tie rule (reference: unspecified torch.topk order): value descending, then index ascending.
+ */
+typedef struct {
+  const float* w0; const float* b0;   /* [8,G,5], [8]   dpn.mlp.0 */
+  const float* w1; const float* b1;   /* [16,8,5], [16] dpn.mlp.2 */
+  const float* w2; const float* b2;   /* [1,16,5], [1]  dpn.mlp.4 */
+} nmrf_seed_weights;
+int nmrf_cost_volume_topk(const float* f1_nhwc, const float* f2_nhwc,   /* [B,h,w,C] */
+                          int B, int h, int w, int C, int G, int D, int K, float eps,
+                          const nmrf_seed_weights* wt,
+                          float* cost_volume,   /* [B*h*w, G, D] */
+                          float* prob,          /* [B*h*w, D]    */
+                          int64_t* seeds,       /* [B*h*w, K] int64, descending prob */
+                          void* stream);
+
+/* ---- A3+A4 gather part: sample_cost + Fourier embed ----------------------------------------
+ * replaces Propagation.sample_cost (NMP.py:618-634) and fourier_coord_embed (NMP.py:35-51).
+ * cost36 row layout: [g*9 + (o+4)] for o in -4..4, zero-padded to ld_cost (>= 36, mult of 16).
+ * enc row layout: 15 sin, 15 cos, raw coordinate, then zero up to 32.
+ */
+int nmrf_prop_gather(const float* cost_volume, const int64_t* seeds, int P, int G, int D, int K,
+                     float normalizer,
+                     float* cost36, int ld_cost,  /* [P*K, ld_cost] */
+                     float* enc32,                /* [P*K, 32] */
+                     void* stream);
+
+/* ---- A6: cross-shaped (stripe) attention with LePE ------------------------------------------
+ * replaces CSWinAttention.forward + get_rpe with split_size 1 (NMP.py:429-505).
+ * qkv: [B*h*w*K, 384] = q|k|v, 4 heads x 32.  Heads 0,1 attend inside image columns
+ * (H_sp=h, W_sp=1), heads 2,3 inside image rows.  Self-edge mask NMP.py:203-208.
+ * get_v0 / get_v1: attns.{0,1}.get_v.weight [64,1,3,3].
+ */
+int nmrf_stripe_attention(const float* qkv, int B, int h, int w, int K,
+                          const float* get_v0, const float* get_v1,
+                          float* out /* [B*h*w*K,128] */, void* stream);
+
+/* ---- A7 tail: labels = relu(hidden . w + b + seed) ------------------------------------------
+ * last layer of dpn.prop_head (DPN.py:65,131-132). hidden: [T,128] (after the two ReLU layers). */
+int nmrf_prop_head_tail(const float* hidden, const float* w /*[128]*/, const float* b /*[1]*/,
+                        const int64_t* seeds, int T, float* labels /*[T]*/, void* stream);
+
+/* ---- A8: warp + group-wise correlation + Fourier embed ---------------------------------------
+ * replaces Inference.sample_fmap/corr (NMP.py:682-720,735-743) and Refinement's K=1 case
+ * (NMP.py:839-846).  Writes on the zero-padded token grid (NMP.py:745-762): Hp,Wp multiples of
+ * the window size, top/left = centre-pad offsets; pad tokens get zeros.
+ * feat row: [f1_cc(64) | warp f2_cc(64) | corr(32)], enc row as in nmrf_prop_gather.
+ */
+int nmrf_warp_corr_embed(const float* f1_cc, const float* f2_cc,   /* [B,h,w,64]  NHWC */
+                         const float* f1_gw, const float* f2_gw,   /* [B,h,w,256] NHWC */
+                         const float* labels,                      /* [B*h*w, K] */
+                         int B, int h, int w, int K, int Hp, int Wp, int top, int left,
+                         float normalizer,
+                         float* feat160, float* enc32,             /* [B*Hp*Wp*K, 160 | 32] */
+                         void* stream);
+/* zero the rows of x[B*Hp*Wp*K, 128] that are padding (label_rep is padded AFTER ffn) */
+int nmrf_zero_pad_rows(float* x, int B, int h, int w, int K, int Hp, int Wp, int top, int left,
+                       void* stream);
+
+/* ---- A10: attention among the K proposals of a pixel ------------------------------------------
+ * core of BasicAttention.forward_pre (NMP.py:97-103). qkv [P*K,384] -> out [P*K,128]. K <= 8. */
+int nmrf_proposal_attention(const float* qkv, int P, int K, float* out, void* stream);
+
+/* ---- A11: (shifted-)window attention with contextual relative position encoding ---------------
+ * replaces WindowAttention.forward (NMP.py:241-289) incl. masks (NMP.py:195-239, 802-826).
+ * qkv [B*Hp*Wp*K, 384]; table = relative_position_enc_table [(2ws-1)^2, 384], column
+ * h*96 + {0:32 Rq, 32:64 Rk, 64:96 Rv}.  shift in {0, ws/2}: done by indexing, no roll.
+ * self_edge_mask: 1 for Inference (K proposals), 0 for Refinement (NMP.py:869).
+ */
+int nmrf_window_attention(const float* qkv, const float* table,
+                          int B, int Hp, int Wp, int K, int ws, int shift, int self_edge_mask,
+                          float* out /* [B*Hp*Wp*K,128] */, void* stream);
+
+/* ---- A12: proposal selection ---------------------------------------------------------------------
+ * replaces NMRF.forward select (NMRF.py:218-232): coarse = relu(label + delta); 8x8 un-shuffle;
+ * argmax over K of score (first max on ties); x2; lower median of each 4x4 block -> disp_curr.
+ * delta, score: [B*Hp*Wp*K, 64] on the PADDED token grid (rows of pad tokens are ignored);
+ * labels [B*h*w, K].  disp_curr [B, 2h, 2w] (units: 1/4-res pixels).
+ */
+int nmrf_select_median(const float* delta, const float* score, const float* labels,
+                       int B, int h, int w, int K, int Hp, int Wp, int top, int left,
+                       float* disp_curr, void* stream);
+
+/* ---- A13 tail: disp = relu(disp_curr + delta) un-shuffled -------------------------------------
+ * replaces NMRF.py:238-245,250-251. delta [B*Hp4*Wp4, 16] on the padded 1/4 grid;
+ * disp_pred [B, 4*h4, 4*w4] (1/4-res units), disp [B, H, W] = 4*disp_pred cropped (unpad).
+ */
+int nmrf_refine_tail(const float* delta, const float* disp_curr,
+                     int B, int h4, int w4, int Hp4, int Wp4, int top, int left, int H, int W,
+                     float* disp_pred, float* disp, void* stream);
+
+/* ---- A14: multi-scale deformable attention forward ---------------------------------------------
+ * replaces ms_deform_attn_forward (ops/src/vision.cpp:13-16, ops/src/ms_deform_attn.h:20-39,
+ * ops/src/cuda/ms_deform_attn_cuda.cu:20-80, ms_deform_im2col_cuda.cuh:237-299).
+ * value [N,S,M,Dh]; spatial_shapes [L,2] int64 (H,W) and level_start_index [L] int64 are HOST
+ * pointers (read once per call); loc [N,Lq,M,L,P,2]; attn [N,Lq,M,L,P]; out [N,Lq,M*Dh].
+ * Any Dh (vectorised kernel when Dh % 4 == 0, as in NMRF: Dh = 8); fp32 only (the reference also
+ * dispatches fp64).
+ */
+int nmrf_ms_deform_attn_forward(const float* value, const int64_t* spatial_shapes_host,
+                                const int64_t* level_start_index_host,
+                                const float* sampling_loc, const float* attn_weight,
+                                int N, int S, int M, int Dh, int L, int Lq, int P,
+                                float* out, void* stream);
+/* same, with spatial_shapes / level_start_index as DEVICE pointers (the reference's convention:
+ * ms_deform_im2col_cuda.cuh:274-277 reads them in the kernel).  No host read => CUDA-graph safe. */
+int nmrf_ms_deform_attn_forward_dev(const float* value, const int64_t* spatial_shapes_dev,
+                                    const int64_t* level_start_index_dev,
+                                    const float* sampling_loc, const float* attn_weight,
+                                    int N, int S, int M, int Dh, int L, int Lq, int P,
+                                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NMRF_B200_H */

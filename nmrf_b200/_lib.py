@@ -1,0 +1,81 @@
+"""ctypes binding of libnmrf_b200.so (C-ABI declared in include/nmrf_b200.h).
+
+The product path has NO fallback: if the shared library is missing, import of this
+module raises, and every entry point raises RuntimeError on a non-zero return code.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
+ABI_VERSION = 1
+
+
+class GemmArgs(Structure):
+    """mirror of nmrf_gemm_args"""
+    _fields_ = [
+        ("X", c_void_p), ("ldx", c_int), ("Kx", c_int),
+        ("E", c_void_p), ("lde", c_int), ("Ke", c_int), ("ediv", c_int),
+        ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
+        ("W", c_void_p), ("ldw", c_int),
+        ("bias", c_void_p),
+        ("R", c_void_p), ("ldr", c_int),
+        ("Y", c_void_p), ("ldy", c_int),
+        ("rows", c_int), ("N", c_int),
+        ("act", c_int),
+    ]
+
+
+class SeedWeights(Structure):
+    """mirror of nmrf_seed_weights"""
+    _fields_ = [("w0", c_void_p), ("b0", c_void_p), ("w1", c_void_p), ("b1", c_void_p),
+                ("w2", c_void_p), ("b2", c_void_p)]
+
+
+# name -> argtypes; every function returns int except the three helpers
+_I, _F, _P = c_int, c_float, c_void_p
+SIGNATURES = {
+    "nmrf_token_gemm": [POINTER(GemmArgs), _P],
+    "nmrf_cost_volume_topk": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, POINTER(SeedWeights), _P, _P, _P, _P],
+    "nmrf_prop_gather": [_P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P],
+    "nmrf_stripe_attention": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
+    "nmrf_prop_head_tail": [_P, _P, _P, _P, _I, _P, _P],
+    "nmrf_warp_corr_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+    "nmrf_zero_pad_rows": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
+    "nmrf_proposal_attention": [_P, _I, _I, _P, _P],
+    "nmrf_window_attention": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "nmrf_select_median": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "nmrf_refine_tail": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "nmrf_ms_deform_attn_forward": [_P, POINTER(c_int64), POINTER(c_int64), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "nmrf_ms_deform_attn_forward_dev": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+}
+HELPERS = {"nmrf_abi_version": (c_int, []), "nmrf_last_error": (c_char_p, []), "nmrf_launch_count": (c_uint64, [])}
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "or `make -C nmrf_b200/csrc`. nmrf_b200 has no CPU/PyTorch fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+for _name, _args in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = c_int
+for _name, (_res, _args) in HELPERS.items():
+    _fn = getattr(lib, _name)
+    _fn.argtypes = _args
+    _fn.restype = _res
+
+if lib.nmrf_abi_version() != ABI_VERSION:
+    raise ImportError(f"libnmrf_b200.so ABI {lib.nmrf_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib.nmrf_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def launch_count():
+    return int(lib.nmrf_launch_count())

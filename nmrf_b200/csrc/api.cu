@@ -1,0 +1,119 @@
+// extern "C" surface of libnmrf_b200.so (see include/nmrf_b200.h).  Argument validation,
+// error text, launch counting; the kernels live in the sibling translation units.
+#include <stdarg.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace nmrf {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return NMRF_OK;
+  set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+  return NMRF_ERR_CUDA;
+}
+
+int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
+int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
+                     float*, float*, int64_t*, cudaStream_t);
+int prop_gather(const float*, const int64_t*, int, int, int, int, float, float*, int, float*, cudaStream_t);
+int prop_head_tail(const float*, const float*, const float*, const int64_t*, int, float*, cudaStream_t);
+int proposal_attention(const float*, int, int, float*, cudaStream_t);
+int window_attention(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
+int stripe_attention(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int,
+                    int, int, float, float*, float*, cudaStream_t);
+int zero_pad_rows(float*, int, int, int, int, int, int, int, int, cudaStream_t);
+int select_median(const float*, const float*, const float*, int, int, int, int, int, int, int, int, float*, cudaStream_t);
+int refine_tail(const float*, const float*, int, int, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const float*, const float*, int, int, int, int,
+                           int, int, int, float*, bool, cudaStream_t);
+
+}  // namespace nmrf
+
+using namespace nmrf;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int nmrf_abi_version(void) { return NMRF_B200_ABI_VERSION; }
+const char* nmrf_last_error(void) { return g_err; }
+uint64_t nmrf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
+  NMRF_REQUIRE(a && a->X && a->W && a->Y, "token_gemm: null pointer");
+  NMRF_REQUIRE(a->rows >= 0 && a->N > 0 && a->N % 4 == 0, "token_gemm: rows=%d N=%d (N must be a multiple of 4)", a->rows, a->N);
+  NMRF_REQUIRE(a->Kx > 0 && a->Kx % 8 == 0 && a->Ke >= 0 && a->Ke % 8 == 0, "token_gemm: Kx=%d Ke=%d must be multiples of 8", a->Kx, a->Ke);
+  NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldw % 4 == 0 && a->ldy % 4 == 0 && a->ldw >= a->Kx + a->Ke, "token_gemm: bad leading dimension");
+  NMRF_REQUIRE((a->Ke == 0) == (a->E == nullptr), "token_gemm: E/Ke mismatch");
+  NMRF_REQUIRE(a->Ke == 0 || (a->ediv >= 1 && a->lde % 4 == 0), "token_gemm: bad ediv/lde");
+  NMRF_REQUIRE((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "token_gemm: LayerNorm needs gamma and beta");
+  NMRF_REQUIRE(a->ln_gamma == nullptr || a->Kx == 128, "token_gemm: LayerNorm prologue needs Kx == 128");
+  NMRF_REQUIRE(a->R == nullptr || a->ldr % 4 == 0, "token_gemm: bad ldr");
+  NMRF_REQUIRE(a->act >= 0 && a->act <= 2, "token_gemm: act=%d", a->act);
+  if (a->rows == 0) return NMRF_OK;
+  return token_gemm_simt(*a, ST(stream));
+}
+
+int nmrf_cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int C, int G, int D, int K, float eps,
+                          const nmrf_seed_weights* wt, float* cost_volume, float* prob, int64_t* seeds, void* stream) {
+  return cost_volume_topk(f1, f2, B, h, w, C, G, D, K, eps, wt, cost_volume, prob, seeds, ST(stream));
+}
+int nmrf_prop_gather(const float* cv, const int64_t* seeds, int P, int G, int D, int K, float normalizer, float* cost36,
+                     int ld_cost, float* enc32, void* stream) {
+  return prop_gather(cv, seeds, P, G, D, K, normalizer, cost36, ld_cost, enc32, ST(stream));
+}
+int nmrf_stripe_attention(const float* qkv, int B, int h, int w, int K, const float* gv0, const float* gv1, float* out,
+                          void* stream) {
+  return stripe_attention(qkv, B, h, w, K, gv0, gv1, out, ST(stream));
+}
+int nmrf_prop_head_tail(const float* hidden, const float* w, const float* b, const int64_t* seeds, int T, float* labels,
+                        void* stream) {
+  return prop_head_tail(hidden, w, b, seeds, T, labels, ST(stream));
+}
+int nmrf_warp_corr_embed(const float* f1_cc, const float* f2_cc, const float* f1_gw, const float* f2_gw,
+                         const float* labels, int B, int h, int w, int K, int Hp, int Wp, int top, int left,
+                         float normalizer, float* feat160, float* enc32, void* stream) {
+  return warp_corr_embed(f1_cc, f2_cc, f1_gw, f2_gw, labels, B, h, w, K, Hp, Wp, top, left, normalizer, feat160, enc32,
+                         ST(stream));
+}
+int nmrf_zero_pad_rows(float* x, int B, int h, int w, int K, int Hp, int Wp, int top, int left, void* stream) {
+  return zero_pad_rows(x, B, h, w, K, Hp, Wp, top, left, ST(stream));
+}
+int nmrf_proposal_attention(const float* qkv, int P, int K, float* out, void* stream) {
+  return proposal_attention(qkv, P, K, out, ST(stream));
+}
+int nmrf_window_attention(const float* qkv, const float* table, int B, int Hp, int Wp, int K, int ws, int shift,
+                          int self_edge_mask, float* out, void* stream) {
+  return window_attention(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask, out, ST(stream));
+}
+int nmrf_select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K, int Hp,
+                       int Wp, int top, int left, float* disp_curr, void* stream) {
+  return select_median(delta, score, labels, B, h, w, K, Hp, Wp, top, left, disp_curr, ST(stream));
+}
+int nmrf_refine_tail(const float* delta, const float* disp_curr, int B, int h4, int w4, int Hp4, int Wp4, int top, int left,
+                     int H, int W, float* disp_pred, float* disp, void* stream) {
+  return refine_tail(delta, disp_curr, B, h4, w4, Hp4, Wp4, top, left, H, W, disp_pred, disp, ST(stream));
+}
+int nmrf_ms_deform_attn_forward(const float* value, const int64_t* shapes, const int64_t* level_start, const float* loc,
+                                const float* attn, int N, int S, int M, int Dh, int L, int Lq, int P, float* out,
+                                void* stream) {
+  return ms_deform_attn_forward(value, shapes, level_start, loc, attn, N, S, M, Dh, L, Lq, P, out, false, ST(stream));
+}
+int nmrf_ms_deform_attn_forward_dev(const float* value, const int64_t* shapes_dev, const int64_t* level_start_dev,
+                                    const float* loc, const float* attn, int N, int S, int M, int Dh, int L, int Lq, int P,
+                                    float* out, void* stream) {
+  return ms_deform_attn_forward(value, shapes_dev, level_start_dev, loc, attn, N, S, M, Dh, L, Lq, P, out, true, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+// Memory-bound stages around the message-passing stacks:
+//   A8  warp_corr_embed  (NMP.py:682-720,735-743 / 839-846)
+//   A9  zero_pad_rows    (NMP.py:756-759: label_rep is zero-padded AFTER the ffn)
+//   A12 select_median    (NMRF.py:218-232)
+//   A13 refine_tail      (NMRF.py:238-245,250-251)
+#include "common.cuh"
+
+namespace nmrf {
+namespace {
+
+// One warp per token of the PADDED grid.  NHWC maps: the 256-ch group-wise map gives each lane
+// its own correlation group (8 consecutive channels = two float4), the 64-ch map a float2.
+__global__ void warp_corr_embed_kernel(const float* __restrict__ f1_cc, const float* __restrict__ f2_cc,
+                                       const float* __restrict__ f1_gw, const float* __restrict__ f2_gw,
+                                       const float* __restrict__ labels, int B, int h, int w, int K,
+                                       int Hp, int Wp, int top, int left, float normalizer,
+                                       float* __restrict__ feat, float* __restrict__ enc) {
+  const int lane = threadIdx.x & 31;
+  const long long tp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long Tp = (long long)B * Hp * Wp * K;
+  if (tp >= Tp) return;
+  const int n = (int)(tp % K);
+  const long long pp = tp / K;
+  const int xp = (int)(pp % Wp), yp = (int)((pp / Wp) % Hp), b = (int)(pp / ((long long)Wp * Hp));
+  const int y = yp - top, x = xp - left;
+  float* frow = feat + tp * 160;
+  float* erow = enc + tp * 32;
+  if (y < 0 || y >= h || x < 0 || x >= w) {
+    for (int i = lane; i < 160; i += 32) frow[i] = 0.f;
+    erow[lane] = 0.f;
+    return;
+  }
+  const size_t pix = ((size_t)b * h + y) * w + x;
+  const float d = labels[pix * K + n];
+  const float xr = (float)x - d;                       // NMP.py:699-702
+  const float xf = floorf(xr);
+  const float a = xr - xf;
+  const int x0 = (int)xf, x1 = x0 + 1;
+  const bool ok0 = x0 >= 0 && x0 <= w - 1, ok1 = x1 >= 0 && x1 <= w - 1;
+  const size_t rowpix = ((size_t)b * h + y) * w;
+  const float w0 = 1.f - a, w1 = a;
+
+  // 256-channel group-wise correlation: lane = group (NMP.py:716-719, cost_group 32)
+  {
+    const float4* p1 = reinterpret_cast<const float4*>(f1_gw + pix * 256 + lane * 8);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a0 = p1[0], a1 = p1[1];
+    float4 t00 = z, t01 = z, t10 = z, t11 = z;
+    if (ok0) { const float4* q = reinterpret_cast<const float4*>(f2_gw + (rowpix + x0) * 256 + lane * 8); t00 = q[0]; t01 = q[1]; }
+    if (ok1) { const float4* q = reinterpret_cast<const float4*>(f2_gw + (rowpix + x1) * 256 + lane * 8); t10 = q[0]; t11 = q[1]; }
+    float s = 0.f;
+    s = fmaf(a0.x, t00.x * w0 + t10.x * w1, s); s = fmaf(a0.y, t00.y * w0 + t10.y * w1, s);
+    s = fmaf(a0.z, t00.z * w0 + t10.z * w1, s); s = fmaf(a0.w, t00.w * w0 + t10.w * w1, s);
+    s = fmaf(a1.x, t01.x * w0 + t11.x * w1, s); s = fmaf(a1.y, t01.y * w0 + t11.y * w1, s);
+    s = fmaf(a1.z, t01.z * w0 + t11.z * w1, s); s = fmaf(a1.w, t01.w * w0 + t11.w * w1, s);
+    frow[128 + lane] = s * 0.125f;
+  }
+  // 64-channel concat features
+  {
+    const float2 c1 = *reinterpret_cast<const float2*>(f1_cc + pix * 64 + lane * 2);
+    float2 t0 = make_float2(0.f, 0.f), t1 = t0;
+    if (ok0) t0 = *reinterpret_cast<const float2*>(f2_cc + (rowpix + x0) * 64 + lane * 2);
+    if (ok1) t1 = *reinterpret_cast<const float2*>(f2_cc + (rowpix + x1) * 64 + lane * 2);
+    *reinterpret_cast<float2*>(frow + lane * 2) = c1;
+    *reinterpret_cast<float2*>(frow + 64 + lane * 2) = make_float2(t0.x * w0 + t1.x * w1, t0.y * w0 + t1.y * w1);
+  }
+  fourier32(d, normalizer, erow, lane);
+}
+
+__global__ void zero_pad_rows_kernel(float* __restrict__ x, int B, int h, int w, int K, int Hp, int Wp,
+                                     int top, int left) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 per thread
+  const long long total = (long long)B * Hp * Wp * K * 32;
+  if (i >= total) return;
+  const long long pp = (i >> 5) / K;
+  const int xp = (int)(pp % Wp), yp = (int)((pp / Wp) % Hp);
+  const int y = yp - top, xx = xp - left;
+  if (y < 0 || y >= h || xx < 0 || xx >= w)
+    reinterpret_cast<float4*>(x)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// One thread per 1/4-resolution pixel: 16 full-resolution sub-pixels, argmax over K, x2, lower median.
+__global__ void select_median_kernel(const float* __restrict__ delta, const float* __restrict__ score,
+                                     const float* __restrict__ labels, int B, int h, int w, int K,
+                                     int Hp, int Wp, int top, int left, float* __restrict__ disp_curr) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int h4 = 2 * h, w4 = 2 * w;
+  if (i >= (long long)B * h4 * w4) return;
+  const int X = (int)(i % w4), Y = (int)((i / w4) % h4), b = (int)(i / ((long long)w4 * h4));
+  const int y = Y >> 1, x = X >> 1, u0 = (Y & 1) * 4, v0 = (X & 1) * 4;
+  const size_t pix = ((size_t)b * h + y) * w + x;
+  const size_t prow = (((size_t)b * Hp + y + top) * Wp + x + left) * K;
+  float val[16], best[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) { val[e] = 0.f; best[e] = -INFINITY; }
+  for (int n = 0; n < K; ++n) {
+    const float lab = labels[pix * K + n];
+    const float* dr = delta + (prow + n) * 64;
+    const float* sr = score + (prow + n) * 64;
+#pragma unroll
+    for (int du = 0; du < 4; ++du) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dr + (u0 + du) * 8 + v0);
+      const float4 s4 = *reinterpret_cast<const float4*>(sr + (u0 + du) * 8 + v0);
+      const float dv[4] = {d4.x, d4.y, d4.z, d4.w};
+      const float sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (sv[e] > best[du * 4 + e]) {              // strict: first maximum wins (torch.max)
+          best[du * 4 + e] = sv[e];
+          val[du * 4 + e] = fmaxf(lab + dv[e], 0.f) * 2.f;
+        }
+      }
+    }
+  }
+  // lower median of 16 = 8th smallest (torch.median): selection by rank counting
+  float med = val[0];
+#pragma unroll
+  for (int a = 0; a < 16; ++a) {
+    int less = 0, eq = 0;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { less += val[c] < val[a]; eq += val[c] == val[a]; }
+    if (less <= 7 && 7 < less + eq) med = val[a];
+  }
+  disp_curr[i] = med;
+}
+
+__global__ void refine_tail_kernel(const float* __restrict__ delta, const float* __restrict__ disp_curr,
+                                   int B, int h4, int w4, int Hp4, int Wp4, int top, int left, int H, int W,
+                                   float* __restrict__ disp_pred, float* __restrict__ disp) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * h4 * w4) return;
+  const int X = (int)(i % w4), Y = (int)((i / w4) % h4), b = (int)(i / ((long long)w4 * h4));
+  const size_t row = ((size_t)b * Hp4 + Y + top) * Wp4 + X + left;
+  const float base = disp_curr[i];
+  const int Hf = 4 * h4, Wf = 4 * w4;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const float4 d4 = *reinterpret_cast<const float4*>(delta + row * 16 + u * 4);
+    float4 o;
+    o.x = fmaxf(base + d4.x, 0.f); o.y = fmaxf(base + d4.y, 0.f);
+    o.z = fmaxf(base + d4.z, 0.f); o.w = fmaxf(base + d4.w, 0.f);
+    const int yy = 4 * Y + u, xx = 4 * X;
+    *reinterpret_cast<float4*>(disp_pred + ((size_t)b * Hf + yy) * Wf + xx) = o;
+    if (yy < H) {
+      float* dst = disp + ((size_t)b * H + yy) * W;
+      if (xx + 0 < W) dst[xx + 0] = o.x * 4.f;
+      if (xx + 1 < W) dst[xx + 1] = o.y * 4.f;
+      if (xx + 2 < W) dst[xx + 2] = o.z * 4.f;
+      if (xx + 3 < W) dst[xx + 3] = o.w * 4.f;
+    }
+  }
+}
+
+}  // namespace
+
+int warp_corr_embed(const float* f1_cc, const float* f2_cc, const float* f1_gw, const float* f2_gw,
+                    const float* labels, int B, int h, int w, int K, int Hp, int Wp, int top, int left,
+                    float normalizer, float* feat160, float* enc32, cudaStream_t stream) {
+  NMRF_REQUIRE(f1_cc && f2_cc && f1_gw && f2_gw && labels && feat160 && enc32, "warp_corr_embed: null pointer");
+  NMRF_REQUIRE(Hp >= h + top && Wp >= w + left && top >= 0 && left >= 0, "warp_corr_embed: bad padding");
+  const long long Tp = (long long)B * Hp * Wp * K;
+  const int threads = 256;
+  const long long blocks = (Tp * 32 + threads - 1) / threads;
+  warp_corr_embed_kernel<<<(unsigned)blocks, threads, 0, stream>>>(f1_cc, f2_cc, f1_gw, f2_gw, labels, B, h, w, K, Hp, Wp,
+                                                                   top, left, normalizer, feat160, enc32);
+  count_launch();
+  return check_launch("warp_corr_embed");
+}
+
+int zero_pad_rows(float* x, int B, int h, int w, int K, int Hp, int Wp, int top, int left, cudaStream_t stream) {
+  NMRF_REQUIRE(x, "zero_pad_rows: null pointer");
+  if (Hp == h && Wp == w) return NMRF_OK;
+  const long long total = (long long)B * Hp * Wp * K * 32;
+  const int threads = 256;
+  zero_pad_rows_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(x, B, h, w, K, Hp, Wp, top, left);
+  count_launch();
+  return check_launch("zero_pad_rows");
+}
+
+int select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K,
+                  int Hp, int Wp, int top, int left, float* disp_curr, cudaStream_t stream) {
+  NMRF_REQUIRE(delta && score && labels && disp_curr, "select_median: null pointer");
+  const long long total = (long long)B * 4 * h * w;
+  const int threads = 128;
+  select_median_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(delta, score, labels, B, h, w, K,
+                                                                                           Hp, Wp, top, left, disp_curr);
+  count_launch();
+  return check_launch("select_median");
+}
+
+int refine_tail(const float* delta, const float* disp_curr, int B, int h4, int w4, int Hp4, int Wp4, int top, int left,
+                int H, int W, float* disp_pred, float* disp, cudaStream_t stream) {
+  NMRF_REQUIRE(delta && disp_curr && disp_pred && disp, "refine_tail: null pointer");
+  NMRF_REQUIRE(H <= 4 * h4 && W <= 4 * w4, "refine_tail: output %dx%d larger than padded %dx%d", H, W, 4 * h4, 4 * w4);
+  const long long total = (long long)B * h4 * w4;
+  const int threads = 128;
+  refine_tail_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(delta, disp_curr, B, h4, w4, Hp4, Wp4,
+                                                                                         top, left, H, W, disp_pred, disp);
+  count_launch();
+  return check_launch("refine_tail");
+}
+
+}  // namespace nmrf

@@ -1,0 +1,293 @@
+"""Host-side driver of the CUDA hot path: weight packing, workspaces and the launch plan.
+
+Everything here is plumbing: torch is used for device memory only.  All arithmetic of the
+path happens in libnmrf_b200.so (see include/nmrf_b200.h); there is no PyTorch fallback.
+
+A `HotPathPlan` is built once per (batch, padded image size) and holds
+  * pre-allocated workspaces (so a forward allocates nothing and is CUDA-graph capturable),
+  * a flat list of (C function, ctypes args) launches.
+Stage order follows NMRF.forward (nmrf/models/NMRF.py:207-245 of the reference).
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, SeedWeights, lib
+
+ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+
+
+@dataclass
+class HotPathConfig:
+    """The hyper-parameters the kernels need (nmrf/config/default.py:37-61)."""
+    max_disp: int = 320
+    num_proposals: int = 4
+    cost_group: int = 4
+    window_size: int = 6
+    refine_window_size: int = 4
+    num_prop_layers: int = 5
+    num_infer_layers: int = 5
+    num_refine_layers: int = 5
+    eps: float = 1e-3                      # DPN.py:51
+
+
+def _f32(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _pad_cols(w, to):
+    """zero-pad the input dimension of an nn.Linear weight [out,in] to `to` columns"""
+    out, k = w.shape
+    if k == to:
+        return _f32(w)
+    p = w.new_zeros(out, to)
+    p[:, :k] = w
+    return _f32(p)
+
+
+def center_pad(n, ws):
+    """NMP.py:747-754: (padded size, leading pad)"""
+    pad = (ws - n % ws) % ws
+    return n + pad, pad // 2
+
+
+class PackedWeights:
+    """Kernel-ready views/copies of the reference state-dict tensors (Appendix C of SURVEY.md).
+
+    Packing is layout only: q/k/v projections sharing an input are stacked along `out`, input
+    dimensions are zero-padded to a multiple of 8 (159 -> 160, 36 -> 48)."""
+
+    def __init__(self, sd, cfg: HotPathConfig):
+        g = lambda k: _f32(sd[k])
+        self.seed = {k: g(f"dpn.mlp.{i}.{n}") for k, (i, n) in
+                     dict(w0=(0, "weight"), b0=(0, "bias"), w1=(2, "weight"), b1=(2, "bias"),
+                          w2=(4, "weight"), b2=(4, "bias")).items()}
+        p = "dpn.propagation"
+        self.ce0_w, self.ce0_b = _pad_cols(sd[p + ".cost_encoder.0.weight"], 48), g(p + ".cost_encoder.0.bias")
+        self.ce2_w, self.ce2_b = g(p + ".cost_encoder.2.weight"), g(p + ".cost_encoder.2.bias")
+        self.pproj_w = _pad_cols(sd[p + ".proj.weight"], 160)
+        self.prop_layers = []
+        for i in range(cfg.num_prop_layers):
+            q = f"{p}.layers.{i}.nmp"
+            wv = _pad_cols(sd[q + ".v.weight"], 192)
+            L = dict(
+                qkv_w=_f32(torch.cat([sd[q + ".q.weight"], sd[q + ".k.weight"], wv], 0)),
+                qkv_b=_f32(torch.cat([sd[q + ".q.bias"], sd[q + ".k.bias"], sd[q + ".v.bias"]], 0)),
+                n1=(g(q + ".norm1.weight"), g(q + ".norm1.bias")),
+                n2=(g(q + ".norm2.weight"), g(q + ".norm2.bias")),
+                proj_w=g(q + ".proj.weight"), proj_b=g(q + ".proj.bias"),
+                gv0=g(q + ".attns.0.get_v.weight"), gv1=g(q + ".attns.1.get_v.weight"),
+                fc1_w=g(q + ".mlp.fc1.weight"), fc1_b=g(q + ".mlp.fc1.bias"),
+                fc2_w=g(q + ".mlp.fc2.weight"), fc2_b=g(q + ".mlp.fc2.bias"))
+            self.prop_layers.append(L)
+        self.prop_norm = (g(p + ".norm.weight"), g(p + ".norm.bias"))
+        self.prop_head = [(g(f"dpn.prop_head.layers.{i}.weight"), g(f"dpn.prop_head.layers.{i}.bias")) for i in range(3)]
+
+        self.stacks = {}
+        for name, n_layers, with_self in (("inference", cfg.num_infer_layers, True),
+                                          ("refinement", cfg.num_refine_layers, False)):
+            S = dict(ffn1_w=g(name + ".ffn.fc1.weight"), ffn1_b=g(name + ".ffn.fc1.bias"),
+                     ffn2_w=g(name + ".ffn.fc2.weight"), ffn2_b=g(name + ".ffn.fc2.bias"),
+                     norm=(g(name + ".norm.weight"), g(name + ".norm.bias")), layers=[])
+            for i in range(n_layers):
+                q = f"{name}.layers.{i}"
+                L = {}
+                if with_self:
+                    s = q + ".self_nmp"
+                    L.update(
+                        s_qkv_w=_f32(torch.cat([_pad_cols(sd[s + ".q.weight"], 160), _pad_cols(sd[s + ".k.weight"], 160),
+                                                _pad_cols(sd[s + ".v.weight"], 160)], 0)),
+                        s_qkv_b=_f32(torch.cat([sd[s + ".q.bias"], sd[s + ".k.bias"], sd[s + ".v.bias"]], 0)),
+                        s_n1=(g(s + ".norm1.weight"), g(s + ".norm1.bias")),
+                        s_proj_w=g(s + ".proj.weight"), s_proj_b=g(s + ".proj.bias"))
+                m = q + ".nmp"
+                L.update(
+                    qkv_w=_pad_cols(sd[m + ".qkv.weight"], 160), qkv_b=g(m + ".qkv.bias"),
+                    n1=(g(m + ".norm1.weight"), g(m + ".norm1.bias")),
+                    n2=(g(m + ".norm2.weight"), g(m + ".norm2.bias")),
+                    table=g(m + ".attn.relative_position_enc_table"),
+                    proj_w=g(m + ".proj.weight"), proj_b=g(m + ".proj.bias"),
+                    fc1_w=g(m + ".mlp.fc1.weight"), fc1_b=g(m + ".mlp.fc1.bias"),
+                    fc2_w=g(m + ".mlp.fc2.weight"), fc2_b=g(m + ".mlp.fc2.bias"))
+                S["layers"].append(L)
+            self.stacks[name] = S
+        self.infer_head = [(g(f"infer_head.layers.{i}.weight"), g(f"infer_head.layers.{i}.bias")) for i in range(3)]
+        self.score_head = (g("infer_score_head.weight"), g("infer_score_head.bias"))
+        self.refine_head = [(g(f"refine_head.layers.{i}.weight"), g(f"refine_head.layers.{i}.bias")) for i in range(3)]
+
+
+class _Launches:
+    """Flat launch list; keeps every ctypes struct and tensor it references alive."""
+
+    def __init__(self):
+        self.calls = []
+        self._keep = []
+
+    def add(self, fn, what, *args):
+        self.calls.append((fn, what, args))
+
+    def keep(self, *objs):
+        self._keep.extend(objs)
+
+    def gemm(self, what, X, W, Y, rows, N, *, Kx=None, E=None, Ke=0, ediv=1, ln=None, bias=None, R=None, act=ACT_NONE):
+        a = GemmArgs()
+        a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), (Kx if Kx is not None else X.shape[1])
+        a.E, a.lde, a.Ke, a.ediv = (E.data_ptr() if E is not None else None), (E.stride(0) if E is not None else 0), Ke, ediv
+        a.ln_gamma, a.ln_beta = (ln[0].data_ptr(), ln[1].data_ptr()) if ln is not None else (None, None)
+        a.W, a.ldw = W.data_ptr(), W.stride(0)
+        a.bias = bias.data_ptr() if bias is not None else None
+        a.R, a.ldr = (R.data_ptr(), R.stride(0)) if R is not None else (None, 0)
+        a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
+        a.rows, a.N, a.act = rows, N, act
+        self.keep(a, X, W, Y, E, ln, bias, R)
+        self.add(lib.nmrf_token_gemm, what, ctypes.byref(a))
+
+    def run(self, stream):
+        for fn, what, args in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, what)
+
+
+class HotPathPlan:
+    """Launch plan for one shape.  B pairs, 1/8 grid h8 x w8, 1/4 grid h4 x w4, output H x W."""
+
+    def __init__(self, pw: PackedWeights, cfg: HotPathConfig, B, C, h8, w8, H, W, device):
+        assert h8 * 8 >= H and w8 * 8 >= W
+        self.cfg, self.B, self.C, self.h8, self.w8, self.H, self.W = cfg, B, C, h8, w8, H, W
+        K, G, D = cfg.num_proposals, cfg.cost_group, cfg.max_disp // 8
+        h4, w4 = 2 * h8, 2 * w8
+        P8, P4 = B * h8 * w8, B * h4 * w4
+        T8 = P8 * K
+        ws, rws = cfg.window_size, cfg.refine_window_size
+        Hp8, top8 = center_pad(h8, ws)
+        Wp8, left8 = center_pad(w8, ws)
+        Hp4, top4 = center_pad(h4, rws)
+        Wp4, left4 = center_pad(w4, rws)
+        T8p, T4p = B * Hp8 * Wp8 * K, B * Hp4 * Wp4
+        Tmax = max(T8, T8p, T4p)
+        self.geom = dict(K=K, G=G, D=D, h4=h4, w4=w4, P8=P8, P4=P4, T8=T8, T8p=T8p, T4p=T4p,
+                         Hp8=Hp8, Wp8=Wp8, top8=top8, left8=left8, Hp4=Hp4, Wp4=Wp4, top4=top4, left4=left4)
+        new = lambda *s, dtype=torch.float32: torch.empty(*s, dtype=dtype, device=device)
+        # ---- inputs (NHWC, filled by the caller before run()) ------------------------------------
+        self.f1_8, self.f2_8 = new(B, h8, w8, C), new(B, h8, w8, C)
+        self.context = new(B, h8, w8, 64)
+        self.cc8 = [new(B, h8, w8, 64), new(B, h8, w8, 64)]
+        self.gw8 = [new(B, h8, w8, 256), new(B, h8, w8, 256)]
+        self.cc4 = [new(B, h4, w4, 64), new(B, h4, w4, 64)]
+        self.gw4 = [new(B, h4, w4, 256), new(B, h4, w4, 256)]
+        # ---- outputs ----------------------------------------------------------------------------
+        self.cost_volume, self.prob = new(P8, G, D), new(P8, D)
+        self.seeds = new(P8, K, dtype=torch.int64)
+        self.labels = new(P8, K)
+        self.disp_curr = new(B, h4, w4)
+        self.disp_pred, self.disp = new(B, 4 * h4, 4 * w4), new(B, H, W)
+        # ---- workspaces -------------------------------------------------------------------------
+        self.x, self.att, self.h1, self.h2 = new(Tmax, 128), new(Tmax, 128), new(Tmax, 128), new(Tmax, 128)
+        self.qkv, self.hid = new(Tmax, 384), new(Tmax, 512)
+        self.feat, self.enc = new(Tmax, 160), new(Tmax, 32)
+        self.cost48 = new(T8, 48)
+        self.delta, self.score = new(Tmax, 64), new(Tmax, 64)
+        self.pw = pw
+        self.launches = _Launches()
+        self._build(pw)
+
+    # -------------------------------------------------------------------------------------------
+    def _mlp_block(self, L_, T, n2, fc1_w, fc1_b, fc2_w, fc2_b, tag):
+        L_.gemm(tag + ".fc1", self.x, fc1_w, self.hid, T, 512, ln=n2, bias=fc1_b, act=ACT_GELU)
+        L_.gemm(tag + ".fc2", self.hid, fc2_w, self.x, T, 128, bias=fc2_b, R=self.x)
+
+    def _build(self, pw):
+        c, g, L_ = self.cfg, self.geom, self.launches
+        B, C, h8, w8 = self.B, self.C, self.h8, self.w8
+        K, G, D = g["K"], g["G"], g["D"]
+        P8, T8 = g["P8"], g["T8"]
+        ptr = lambda t: t.data_ptr()
+
+        # A1+A2 -------------------------------------------------------------------------------------
+        sw = SeedWeights(*[ptr(pw.seed[k]) for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
+        L_.keep(sw)
+        L_.add(lib.nmrf_cost_volume_topk, "cost_volume_topk", ptr(self.f1_8), ptr(self.f2_8), B, h8, w8, C, G, D, K,
+               c.eps, ctypes.byref(sw), ptr(self.cost_volume), ptr(self.prob), ptr(self.seeds))
+        # A3+A4 -------------------------------------------------------------------------------------
+        L_.add(lib.nmrf_prop_gather, "prop_gather", ptr(self.cost_volume), ptr(self.seeds), P8, G, D, K, 3.14 / 64,
+               ptr(self.cost48), 48, ptr(self.enc))
+        L_.gemm("cost_encoder.0", self.cost48, pw.ce0_w, self.h1, T8, 128, bias=pw.ce0_b, act=ACT_GELU)
+        L_.gemm("cost_encoder.2", self.h1, pw.ce2_w, self.h2, T8, 128, bias=pw.ce2_b)
+        L_.gemm("propagation.proj", self.h2, pw.pproj_w, self.x, T8, 128, E=self.enc, Ke=32)
+        # A5+A6 -------------------------------------------------------------------------------------
+        ctx = self.context.view(P8, 64)
+        for i, w in enumerate(pw.prop_layers):
+            t = f"prop{i}"
+            L_.gemm(t + ".qkv", self.x, w["qkv_w"], self.qkv, T8, 384, E=ctx, Ke=64, ediv=K, ln=w["n1"], bias=w["qkv_b"])
+            L_.add(lib.nmrf_stripe_attention, t + ".stripe", ptr(self.qkv), B, h8, w8, K, ptr(w["gv0"]), ptr(w["gv1"]),
+                   ptr(self.att))
+            L_.gemm(t + ".proj", self.att, w["proj_w"], self.x, T8, 128, bias=w["proj_b"], R=self.x)
+            self._mlp_block(L_, T8, w["n2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], t)
+        # A7 ----------------------------------------------------------------------------------------
+        (w0, b0), (w1, b1), (w2, b2) = pw.prop_head
+        L_.gemm("prop_head.0", self.x, w0, self.h1, T8, 128, ln=pw.prop_norm, bias=b0, act=ACT_RELU)
+        L_.gemm("prop_head.1", self.h1, w1, self.h2, T8, 128, bias=b1, act=ACT_RELU)
+        L_.add(lib.nmrf_prop_head_tail, "prop_head.2", ptr(self.h2), ptr(w2), ptr(b2), ptr(self.seeds), T8, ptr(self.labels))
+
+        # A8-A12: inference @1/8 --------------------------------------------------------------------
+        self._stack(L_, pw.stacks["inference"], "inference", self.labels, self.cc8, self.gw8, h8, w8, K,
+                    g["Hp8"], g["Wp8"], g["top8"], g["left8"], c.window_size, 3.14 / 64, True)
+        T8p = g["T8p"]
+        (w0, b0), (w1, b1), (w2, b2) = pw.infer_head
+        nrm = pw.stacks["inference"]["norm"]
+        L_.gemm("infer_head.0", self.x, w0, self.h1, T8p, 128, ln=nrm, bias=b0, act=ACT_RELU)
+        L_.gemm("infer_head.1", self.h1, w1, self.h2, T8p, 128, bias=b1, act=ACT_RELU)
+        L_.gemm("infer_head.2", self.h2, w2, self.delta, T8p, 64, bias=b2)
+        # 0.25 * score (NMRF.py:220) does not change the argmax: the exact power-of-two scale is dropped
+        L_.gemm("infer_score_head", self.x, pw.score_head[0], self.score, T8p, 64, ln=nrm, bias=pw.score_head[1])
+        L_.add(lib.nmrf_select_median, "select_median", ptr(self.delta), ptr(self.score), ptr(self.labels), B, h8, w8, K,
+               g["Hp8"], g["Wp8"], g["top8"], g["left8"], ptr(self.disp_curr))
+
+        # A13: refinement @1/4 ----------------------------------------------------------------------
+        h4, w4 = g["h4"], g["w4"]
+        self._stack(L_, pw.stacks["refinement"], "refinement", self.disp_curr, self.cc4, self.gw4, h4, w4, 1,
+                    g["Hp4"], g["Wp4"], g["top4"], g["left4"], c.refine_window_size, 3.14 / 128, False)
+        T4p = g["T4p"]
+        (w0, b0), (w1, b1), (w2, b2) = pw.refine_head
+        nrm = pw.stacks["refinement"]["norm"]
+        L_.gemm("refine_head.0", self.x, w0, self.h1, T4p, 128, ln=nrm, bias=b0, act=ACT_RELU)
+        L_.gemm("refine_head.1", self.h1, w1, self.h2, T4p, 128, bias=b1, act=ACT_RELU)
+        L_.gemm("refine_head.2", self.h2, w2, self.delta, T4p, 16, bias=b2)
+        L_.add(lib.nmrf_refine_tail, "refine_tail", ptr(self.delta), ptr(self.disp_curr), B, h4, w4, g["Hp4"], g["Wp4"],
+               g["top4"], g["left4"], self.H, self.W, ptr(self.disp_pred), ptr(self.disp))
+
+    def _stack(self, L_, S, name, labels, cc, gw, h, w, K, Hp, Wp, top, left, ws, normalizer, with_self):
+        B = self.B
+        ptr = lambda t: t.data_ptr()
+        Tp = B * Hp * Wp * K
+        L_.add(lib.nmrf_warp_corr_embed, name + ".embed", ptr(cc[0]), ptr(cc[1]), ptr(gw[0]), ptr(gw[1]), ptr(labels),
+               B, h, w, K, Hp, Wp, top, left, normalizer, ptr(self.feat), ptr(self.enc))
+        L_.gemm(name + ".ffn.fc1", self.feat, S["ffn1_w"], self.h1, Tp, 128, bias=S["ffn1_b"], act=ACT_GELU)
+        L_.gemm(name + ".ffn.fc2", self.h1, S["ffn2_w"], self.x, Tp, 128, bias=S["ffn2_b"])
+        if Hp != h or Wp != w:
+            L_.add(lib.nmrf_zero_pad_rows, name + ".zero_pad", ptr(self.x), B, h, w, K, Hp, Wp, top, left)
+        for i, wt in enumerate(S["layers"]):
+            t = f"{name}{i}"
+            shift = 0 if i % 2 == 0 else ws // 2                     # NMRF.py:72,96
+            if with_self:
+                L_.gemm(t + ".self.qkv", self.x, wt["s_qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["s_n1"],
+                        bias=wt["s_qkv_b"])
+                L_.add(lib.nmrf_proposal_attention, t + ".self.attn", ptr(self.qkv), Tp // K, K, ptr(self.att))
+                L_.gemm(t + ".self.proj", self.att, wt["s_proj_w"], self.x, Tp, 128, bias=wt["s_proj_b"], R=self.x)
+            L_.gemm(t + ".qkv", self.x, wt["qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["n1"], bias=wt["qkv_b"])
+            L_.add(lib.nmrf_window_attention, t + ".window", ptr(self.qkv), ptr(wt["table"]), B, Hp, Wp, K, ws, shift,
+                   1 if with_self else 0, ptr(self.att))
+            L_.gemm(t + ".proj", self.att, wt["proj_w"], self.x, Tp, 128, bias=wt["proj_b"], R=self.x)
+            self._mlp_block(L_, Tp, wt["n2"], wt["fc1_w"], wt["fc1_b"], wt["fc2_w"], wt["fc2_b"], t)
+
+    # -------------------------------------------------------------------------------------------
+    def run(self):
+        """Launch the whole hot path on the current stream (inputs already copied in)."""
+        self.launches.run(torch.cuda.current_stream().cuda_stream)
+
+    @property
+    def num_launches(self):
+        return len(self.launches.calls)

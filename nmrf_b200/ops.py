@@ -1,0 +1,152 @@
+"""Tensor-level wrappers of the C entry points (PyTorch tensors in, PyTorch tensors out).
+
+One function per `nmrf_*` symbol of include/nmrf_b200.h; each checks device/dtype/contiguity,
+allocates the outputs and launches on the current stream.  `hotpath.HotPathPlan` bypasses these
+(pre-built ctypes argument lists); they exist for users who want a single operator, and for the
+stage-level parity tests.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, SeedWeights, lib
+
+
+def _chk(t, name, dtype=torch.float32):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (nmrf_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} tensor has to be contiguous")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None):
+    """Y = act(concat(LN?(X), E[r // ediv]) @ W.T + bias) (+ R).  X [rows,Kx], E [*,Ke], W [N,>=Kx+Ke]."""
+    for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R)):
+        _chk(t, n)
+    rows, Kx = X.shape
+    N = W.shape[0]
+    Y = out if out is not None else torch.empty(rows, N, device=X.device, dtype=torch.float32)
+    a = GemmArgs()
+    a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), Kx
+    a.E, a.lde, a.Ke, a.ediv = _p(E), (E.stride(0) if E is not None else 0), (E.shape[1] if E is not None else 0), ediv
+    a.ln_gamma, a.ln_beta = (_p(ln[0]), _p(ln[1])) if ln is not None else (None, None)
+    a.W, a.ldw = W.data_ptr(), W.stride(0)
+    a.bias = _p(bias)
+    a.R, a.ldr = _p(R), (R.stride(0) if R is not None else 0)
+    a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
+    a.rows, a.N, a.act = rows, N, act
+    _lib.check(lib.nmrf_token_gemm(ctypes.byref(a), _stream()), "token_gemm")
+    return Y
+
+
+def cost_volume_topk(f1_nhwc, f2_nhwc, conv_w, D, K, G=4, eps=1e-3):
+    """conv_w: dict w0,b0,w1,b1,w2,b2 (dpn.mlp.{0,2,4}).  -> cost_volume [P,G,D], prob [P,D], seeds [P,K] int64"""
+    _chk(f1_nhwc, "f1"); _chk(f2_nhwc, "f2")
+    for k, t in conv_w.items():
+        _chk(t, k)
+    B, h, w, C = f1_nhwc.shape
+    P = B * h * w
+    dev = f1_nhwc.device
+    cv = torch.empty(P, G, D, device=dev)
+    prob = torch.empty(P, D, device=dev)
+    seeds = torch.empty(P, K, device=dev, dtype=torch.int64)
+    sw = SeedWeights(*[conv_w[k].data_ptr() for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
+    _lib.check(lib.nmrf_cost_volume_topk(f1_nhwc.data_ptr(), f2_nhwc.data_ptr(), B, h, w, C, G, D, K, eps,
+                                         ctypes.byref(sw), cv.data_ptr(), prob.data_ptr(), seeds.data_ptr(), _stream()),
+               "cost_volume_topk")
+    return cv, prob, seeds
+
+
+def prop_gather(cost_volume, seeds, normalizer=3.14 / 64, ld_cost=48):
+    _chk(cost_volume, "cost_volume"); _chk(seeds, "seeds", torch.int64)
+    P, G, D = cost_volume.shape
+    K = seeds.shape[1]
+    cost = torch.empty(P * K, ld_cost, device=seeds.device)
+    enc = torch.empty(P * K, 32, device=seeds.device)
+    _lib.check(lib.nmrf_prop_gather(cost_volume.data_ptr(), seeds.data_ptr(), P, G, D, K, normalizer, cost.data_ptr(),
+                                    ld_cost, enc.data_ptr(), _stream()), "prop_gather")
+    return cost, enc
+
+
+def stripe_attention(qkv, B, h, w, K, get_v0, get_v1):
+    _chk(qkv, "qkv"); _chk(get_v0, "get_v0"); _chk(get_v1, "get_v1")
+    out = torch.empty(qkv.shape[0], 128, device=qkv.device)
+    _lib.check(lib.nmrf_stripe_attention(qkv.data_ptr(), B, h, w, K, get_v0.data_ptr(), get_v1.data_ptr(),
+                                         out.data_ptr(), _stream()), "stripe_attention")
+    return out
+
+
+def prop_head_tail(hidden, w, b, seeds):
+    _chk(hidden, "hidden"); _chk(w, "w"); _chk(b, "b"); _chk(seeds, "seeds", torch.int64)
+    T = hidden.shape[0]
+    labels = torch.empty(T, device=hidden.device)
+    _lib.check(lib.nmrf_prop_head_tail(hidden.data_ptr(), w.data_ptr(), b.data_ptr(), seeds.data_ptr(), T,
+                                       labels.data_ptr(), _stream()), "prop_head_tail")
+    return labels
+
+
+def warp_corr_embed(f1_cc, f2_cc, f1_gw, f2_gw, labels, K, Hp, Wp, top, left, normalizer):
+    """NHWC maps [B,h,w,64|256]; labels [B*h*w,K] -> feat [B*Hp*Wp*K,160], enc [.,32] on the padded grid"""
+    for n, t in (("f1_cc", f1_cc), ("f2_cc", f2_cc), ("f1_gw", f1_gw), ("f2_gw", f2_gw), ("labels", labels)):
+        _chk(t, n)
+    B, h, w, _ = f1_cc.shape
+    Tp = B * Hp * Wp * K
+    feat = torch.empty(Tp, 160, device=labels.device)
+    enc = torch.empty(Tp, 32, device=labels.device)
+    _lib.check(lib.nmrf_warp_corr_embed(f1_cc.data_ptr(), f2_cc.data_ptr(), f1_gw.data_ptr(), f2_gw.data_ptr(),
+                                        labels.data_ptr(), B, h, w, K, Hp, Wp, top, left, normalizer, feat.data_ptr(),
+                                        enc.data_ptr(), _stream()), "warp_corr_embed")
+    return feat, enc
+
+
+def zero_pad_rows(x, B, h, w, K, Hp, Wp, top, left):
+    _chk(x, "x")
+    _lib.check(lib.nmrf_zero_pad_rows(x.data_ptr(), B, h, w, K, Hp, Wp, top, left, _stream()), "zero_pad_rows")
+    return x
+
+
+def proposal_attention(qkv, K):
+    _chk(qkv, "qkv")
+    out = torch.empty(qkv.shape[0], 128, device=qkv.device)
+    _lib.check(lib.nmrf_proposal_attention(qkv.data_ptr(), qkv.shape[0] // K, K, out.data_ptr(), _stream()),
+               "proposal_attention")
+    return out
+
+
+def window_attention(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask):
+    _chk(qkv, "qkv"); _chk(table, "table")
+    out = torch.empty(qkv.shape[0], 128, device=qkv.device)
+    _lib.check(lib.nmrf_window_attention(qkv.data_ptr(), table.data_ptr(), B, Hp, Wp, K, ws, shift,
+                                         1 if self_edge_mask else 0, out.data_ptr(), _stream()), "window_attention")
+    return out
+
+
+def select_median(delta, score, labels, B, h, w, K, Hp, Wp, top, left):
+    _chk(delta, "delta"); _chk(score, "score"); _chk(labels, "labels")
+    out = torch.empty(B, 2 * h, 2 * w, device=delta.device)
+    _lib.check(lib.nmrf_select_median(delta.data_ptr(), score.data_ptr(), labels.data_ptr(), B, h, w, K, Hp, Wp, top,
+                                      left, out.data_ptr(), _stream()), "select_median")
+    return out
+
+
+def refine_tail(delta, disp_curr, Hp4, Wp4, top, left, H, W):
+    _chk(delta, "delta"); _chk(disp_curr, "disp_curr")
+    B, h4, w4 = disp_curr.shape
+    disp_pred = torch.empty(B, 4 * h4, 4 * w4, device=delta.device)
+    disp = torch.empty(B, H, W, device=delta.device)
+    _lib.check(lib.nmrf_refine_tail(delta.data_ptr(), disp_curr.data_ptr(), B, h4, w4, Hp4, Wp4, top, left, H, W,
+                                    disp_pred.data_ptr(), disp.data_ptr(), _stream()), "refine_tail")
+    return disp_pred, disp

@@ -123,10 +123,12 @@ class _Launches:
 
     def __init__(self):
         self.calls = []
+        self.cost = []          # algorithmic (flops, HBM bytes) per launch, for the roofline report
         self._keep = []
 
-    def add(self, fn, what, *args):
+    def add(self, fn, what, *args, flops=0.0, bytes=0.0):
         self.calls.append((fn, what, args))
+        self.cost.append((flops, bytes))
 
     def keep(self, *objs):
         self._keep.extend(objs)
@@ -142,13 +144,36 @@ class _Launches:
         a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
         a.rows, a.N, a.act = rows, N, act
         self.keep(a, X, W, Y, E, ln, bias, R)
-        self.add(lib.nmrf_token_gemm, what, ctypes.byref(a))
+        # algorithmic work: 2*MAC flops; activations read+written once (weights are L2-resident, excluded)
+        flops = 2.0 * rows * N * (a.Kx + Ke)
+        nbytes = 4.0 * (rows * a.Kx + (rows // max(ediv, 1)) * Ke + rows * N * (2 if R is not None else 1))
+        self.add(lib.nmrf_token_gemm, what, ctypes.byref(a), flops=flops, bytes=nbytes)
 
     def run(self, stream):
         for fn, what, args in self.calls:
             rc = fn(*args, stream)
             if rc != 0:
                 _lib.check(rc, what)
+
+    def run_timed(self, reps=3):
+        """eager run with a CUDA-event pair around every launch (on the launching stream).
+        Returns [(what, symbol, ms, flops, bytes)] with ms = best of `reps`."""
+        cur = torch.cuda.current_stream()
+        stream = cur.cuda_stream
+        best = [float("inf")] * len(self.calls)
+        for _ in range(reps):
+            evs = []
+            for fn, what, args in self.calls:
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record(cur)
+                rc = fn(*args, stream)
+                e.record(cur)
+                if rc != 0:
+                    _lib.check(rc, what)
+                evs.append((s, e))
+            torch.cuda.synchronize()
+            best = [min(b, s.elapsed_time(e)) for b, (s, e) in zip(best, evs)]
+        return [(what, fn.__name__, ms, c[0], c[1]) for (fn, what, _), ms, c in zip(self.calls, best, self.cost)]
 
 
 class HotPathPlan:

@@ -113,8 +113,37 @@ def oracle_forward_fn(sd):
     return lambda a, b: O.forward(sd, cfg, a, b)
 
 
+def pick_cpu_threads():
+    """all host cores the reference's PyTorch-CPU forward can actually use: intra-op parallelism over the small
+    per-window / per-stripe tensors of this model stops scaling (and then collapses) well below a 128-core host,
+    so the thread count is calibrated once on a short forward and the best one is used and reported."""
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, ncpu) if c <= ncpu})
+    if len(cands) == 1:
+        return cands[0]
+    from nmrf_b200.synthetic import synthetic_pair
+    from oracle import nmrf_oracle as O
+    import nmrf_b200
+    cfg = nmrf_b200.get_cfg()
+    cfg.DPN.MAX_DISP, cfg.NMP.NUM_PROP_LAYERS, cfg.NMP.NUM_INFER_LAYERS, cfg.NMP.NUM_REFINE_LAYERS = 192, 1, 1, 1
+    from nmrf_b200.synthetic import synthetic_state_dict
+    sd = synthetic_state_dict(nmrf_b200.build_model(cfg).state_dict(), 0, "reference")
+    ocfg = O.OracleConfig(max_disp=192, num_proposals=4, num_prop_layers=1, num_infer_layers=1, num_refine_layers=1, taps=None)
+    a, b = synthetic_pair(1, 272, 480, 192, 0)
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        torch.set_num_threads(c)
+        O.forward(sd, ocfg, a, b)
+        t0 = time.perf_counter()
+        O.forward(sd, ocfg, a, b)
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = c, t
+    return best
+
+
 def time_cpu(fn, pairs, steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(pick_cpu_threads())
     for i in range(warmup):
         fn(*pairs[i % len(pairs)])
     ts = []

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NMRF_B200_ABI_VERSION 1
+#define NMRF_B200_ABI_VERSION 2
 
 enum {
   NMRF_OK = 0,
@@ -56,8 +56,15 @@ typedef struct {
   float* Y; int ldy;
   int rows; int N;
   int act;                                     /* 0 none, 1 ReLU, 2 GELU (erf) */
+  /* Tensor-core path (tcgen05 kind::tf32, error-compensated 3xTF32, fp32-level accuracy): set W to the
+   * hi part and W_lo to the lo part produced by nmrf_split_tf32 from a weight whose input dimension is
+   * zero-padded to a multiple of 32 (ldw % 32 == 0); N % 16 == 0, N <= 512.  W_lo == NULL selects the
+   * exact-fp32 FMA kernel. */
+  const float* W_lo;
 } nmrf_gemm_args;
 int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
+/* hi = rna_tf32(w), lo = rna_tf32(w - hi), elementwise over n floats (device pointers) */
+int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
 
 /* ---- A1+A2: cost volume + seed extraction ------------------------------------------------
  * replaces build_correlation_volume (nmrf/models/submodule.py:4-23) and DPN.forward step 1

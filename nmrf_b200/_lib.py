@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class GemmArgs(Structure):
@@ -24,6 +24,7 @@ class GemmArgs(Structure):
         ("Y", c_void_p), ("ldy", c_int),
         ("rows", c_int), ("N", c_int),
         ("act", c_int),
+        ("W_lo", c_void_p),
     ]
 
 
@@ -37,6 +38,7 @@ class SeedWeights(Structure):
 _I, _F, _P = c_int, c_float, c_void_p
 SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
+    "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
     "nmrf_cost_volume_topk": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, POINTER(SeedWeights), _P, _P, _P, _P],
     "nmrf_prop_gather": [_P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P],
     "nmrf_stripe_attention": [_P, _I, _I, _I, _I, _P, _P, _P, _P],

@@ -24,6 +24,8 @@ int check_launch(const char* what) {
 }
 
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
+int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
+int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
                      float*, float*, int64_t*, cudaStream_t);
 int prop_gather(const float*, const int64_t*, int, int, int, int, float, float*, int, float*, cudaStream_t);
@@ -62,7 +64,16 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
   NMRF_REQUIRE(a->R == nullptr || a->ldr % 4 == 0, "token_gemm: bad ldr");
   NMRF_REQUIRE(a->act >= 0 && a->act <= 2, "token_gemm: act=%d", a->act);
   if (a->rows == 0) return NMRF_OK;
+  if (a->W_lo) {
+    const int kpad = ((a->Kx + a->Ke + 31) / 32) * 32;
+    NMRF_REQUIRE(a->N % 16 == 0 && a->N <= 512, "token_gemm(tc): N=%d must be a multiple of 16, <= 512", a->N);
+    NMRF_REQUIRE(a->ldw % 32 == 0 && a->ldw >= kpad, "token_gemm(tc): ldw=%d must be a multiple of 32 and >= %d", a->ldw, kpad);
+    return token_gemm_tc(*a, a->W_lo, ST(stream));
+  }
   return token_gemm_simt(*a, ST(stream));
+}
+int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
+  return split_tf32(w, hi, lo, (long long)n, ST(stream));
 }
 
 int nmrf_cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int C, int G, int D, int K, float eps,

@@ -49,12 +49,16 @@ __global__ void proposal_attention_kernel(const float* __restrict__ qkv, int P, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// A11: window attention.  One CTA = one head of `wpc` consecutive windows (the head's slice of
-// the relative-position table is staged once per CTA).  Token slot t=(pl,n), pl = ly*ws+lx.
+// A11: window attention.  One CTA = one head of `wpc` windows processed TOGETHER (the head's slice of
+// the relative-position table is staged once per CTA; small windows fill the CTA).  Token slot
+// t=(pl,n), pl = ly*ws+lx.
 //   logits[i,j] = s q_i.k_j + s q_i.Rk[rel(pi,pj)] + s k_j.Rq[rel(pi,pj)] + mask     (NMP.py:263-275)
 //   out_i       = sum_j A_ij v_j + sum_pj (sum_n A_i,(pj,n)) Rv[rel(pi,pj)]          (NMP.py:282)
 // The two RPE logit terms are evaluated per (token, pixel) pair once (QR, KR: T x P tables)
 // instead of per (token, token) pair; the Rv term uses the per-pixel bucket sums of A.
+// Register blocking: a warp owns R query rows at a time and each lane NCH key columns, so the QK^T
+// inner loop issues R*NCH independent FMAs per (R/2 + NCH) shared-memory loads, and the A.V loop
+// R FMAs per (1 + R/2) loads.
 // ------------------------------------------------------------------------------------------------
 struct WinParams {
   const float* qkv; const float* table; float* out;
@@ -64,140 +68,199 @@ struct WinParams {
 constexpr int WIN_THREADS = 256;
 constexpr int WIN_WARPS = WIN_THREADS / 32;
 
+template <int R, int NCH>
 __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const WinParams p) {
   extern __shared__ __align__(16) float smem[];
   const int ws = p.ws, K = p.K;
-  const int P = ws * ws, Tw = P * K, R = (2 * ws - 1) * (2 * ws - 1);
-  const int TwP = Tw + 1;
-  float* sRq = smem;                 // [R][32]  (pre-scaled)
-  float* sRk = sRq + R * 32;         // [R][32]
-  float* sRv = sRk + R * 32;         // [R][32]
-  float* qs = sRv + R * 32;          // [Tw][32] (pre-scaled)
-  float* kT = qs + Tw * 32;          // [32][Tw+1]
-  float* vs = kT + 32 * TwP;         // [Tw][32]
-  float* QR = vs + Tw * 32;          // [Tw][P]
-  float* KR = QR + Tw * P;           // [Tw][P]
-  float* rowbuf = KR + Tw * P;       // [WARPS][Tw]
-  float* abuf = rowbuf + WIN_WARPS * Tw;   // [WARPS][P]
-  int* tok_row = reinterpret_cast<int*>(abuf + WIN_WARPS * P);   // [Tw] global token row
-  int* reg = tok_row + Tw;           // [P] Swin region id (rolled coordinates)
+  const int P = ws * ws, Tw = P * K, NR = (2 * ws - 1) * (2 * ws - 1);
+  const int TT = p.wpc * Tw;           // token slots of all windows of this CTA
+  const int TP = TT + 2;               // even row stride: 8-byte aligned float2 broadcasts, conflict-free columns
+  float* sRq = smem;                   // [NR][32]  (pre-scaled)
+  float* sRk = sRq + NR * 32;          // [NR][32]
+  float* sRv = sRk + NR * 32;          // [NR][32]
+  float* qT = sRv + NR * 32;           // [32][TP]  (pre-scaled)
+  float* kT = qT + 32 * TP;            // [32][TP]
+  float* vs = kT + 32 * TP;            // [TT][32]
+  float* QR = vs + TT * 32;            // [TT][P]
+  float* KR = QR + TT * P;             // [TT][P]
+  float* pbuf = KR + TT * P;           // [WARPS][Tw][R]   un-normalised probabilities, transposed
+  float* abuf = pbuf + WIN_WARPS * Tw * R;   // [WARPS][P][R]  per-pixel bucket sums
+  int* tok_row = reinterpret_cast<int*>(abuf + WIN_WARPS * P * R);   // [TT] global token row
+  int* reg = tok_row + TT;             // [wpc*P] Swin region id (rolled coordinates)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y;
+  const int w_begin = blockIdx.x * p.wpc;
+  const int nw = min(p.wpc, p.nwin - w_begin);      // windows actually present
 
-  for (int i = tid; i < R * 32; i += WIN_THREADS) {
+  for (int i = tid; i < NR * 32; i += WIN_THREADS) {
     const int r = i >> 5, d = i & 31;
     const float* row = p.table + (size_t)r * kQkv + head * 96;
     sRq[i] = row[d] * kScale;
     sRk[i] = row[32 + d];
     sRv[i] = row[64 + d];
   }
-
-  const int w_begin = blockIdx.x * p.wpc;
-  const int w_end = min(w_begin + p.wpc, p.nwin);
-  for (int win = w_begin; win < w_end; ++win) {
+  for (int t = tid; t < TT; t += WIN_THREADS) {
+    const int wl = t / Tw, tl = t % Tw;
+    const int win = min(w_begin + wl, p.nwin - 1);   // slots of absent windows alias the last one (never stored)
     const int b = win / (p.nwy * p.nwx);
     const int wy = (win / p.nwx) % p.nwy, wx = win % p.nwx;
-    __syncthreads();   // previous window fully consumed (and tables visible on the first pass)
-    for (int t = tid; t < Tw; t += WIN_THREADS) {
-      const int pl = t / K, n = t % K;
-      const int yr = wy * ws + pl / ws, xr = wx * ws + pl % ws;          // rolled coordinates
-      const int y = (yr + p.shift) % p.Hp, x = (xr + p.shift) % p.Wp;    // NMP.py:249-250
-      tok_row[t] = ((b * p.Hp + y) * p.Wp + x) * K + n;
-      if (n == 0) {
-        int r = 0;
-        if (p.shift > 0) {                                               // NMP.py:221-232
-          const int ry = (yr >= p.Hp - ws) + (yr >= p.Hp - p.shift);
-          const int rx = (xr >= p.Wp - ws) + (xr >= p.Wp - p.shift);
-          r = ry * 3 + rx;
-        }
-        reg[pl] = r;
+    const int pl = tl / K, n = tl % K;
+    const int yr = wy * ws + pl / ws, xr = wx * ws + pl % ws;          // rolled coordinates
+    const int y = (yr + p.shift) % p.Hp, x = (xr + p.shift) % p.Wp;    // NMP.py:249-250
+    tok_row[t] = ((b * p.Hp + y) * p.Wp + x) * K + n;
+    if (n == 0) {
+      int r = 0;
+      if (p.shift > 0) {                                               // NMP.py:221-232
+        const int ry = (yr >= p.Hp - ws) + (yr >= p.Hp - p.shift);
+        const int rx = (xr >= p.Wp - ws) + (xr >= p.Wp - p.shift);
+        r = ry * 3 + rx;
       }
+      reg[wl * P + pl] = r;
     }
-    __syncthreads();
-    for (int i = tid; i < Tw * 8; i += WIN_THREADS) {                    // float4 per thread
-      const int t = i >> 3, c = (i & 7) * 4;
-      const float* src = p.qkv + (size_t)tok_row[t] * kQkv + head * 32 + c;
-      const float4 q = *reinterpret_cast<const float4*>(src);
-      const float4 k = *reinterpret_cast<const float4*>(src + 128);
-      const float4 v = *reinterpret_cast<const float4*>(src + 256);
-      *reinterpret_cast<float4*>(qs + t * 32 + c) = make_float4(q.x * kScale, q.y * kScale, q.z * kScale, q.w * kScale);
-      kT[(c + 0) * TwP + t] = k.x; kT[(c + 1) * TwP + t] = k.y;
-      kT[(c + 2) * TwP + t] = k.z; kT[(c + 3) * TwP + t] = k.w;
-      *reinterpret_cast<float4*>(vs + t * 32 + c) = v;
-    }
-    __syncthreads();
-    // QR[t][pp] = (s q_t).Rk[rel(p_t,pp)]     KR[t][pp] = k_t.(s Rq[rel(pp,p_t)])
-    for (int i = tid; i < Tw * P; i += WIN_THREADS) {
-      const int t = i / P, pp = i % P;
-      const int pt = t / K;
-      const int dy = pt / ws - pp / ws, dx = pt % ws - pp % ws;
-      const float* rk = sRk + ((dy + ws - 1) * (2 * ws - 1) + (dx + ws - 1)) * 32;
-      const float* rq = sRq + ((-dy + ws - 1) * (2 * ws - 1) + (-dx + ws - 1)) * 32;
-      float a = 0.f, c = 0.f;
+  }
+  __syncthreads();
+  for (int i = tid; i < TT * 8; i += WIN_THREADS) {                    // one float4 of q, k, v per thread
+    const int t = i >> 3, c = (i & 7) * 4;
+    const float* src = p.qkv + (size_t)tok_row[t] * kQkv + head * 32 + c;
+    const float4 q = *reinterpret_cast<const float4*>(src);
+    const float4 k = *reinterpret_cast<const float4*>(src + 128);
+    const float4 v = *reinterpret_cast<const float4*>(src + 256);
+    qT[(c + 0) * TP + t] = q.x * kScale; qT[(c + 1) * TP + t] = q.y * kScale;
+    qT[(c + 2) * TP + t] = q.z * kScale; qT[(c + 3) * TP + t] = q.w * kScale;
+    kT[(c + 0) * TP + t] = k.x; kT[(c + 1) * TP + t] = k.y;
+    kT[(c + 2) * TP + t] = k.z; kT[(c + 3) * TP + t] = k.w;
+    *reinterpret_cast<float4*>(vs + t * 32 + c) = v;
+  }
+  __syncthreads();
+  // QR[t][pp] = (s q_t).Rk[rel(p_t,pp)]     KR[t][pp] = k_t.(s Rq[rel(pp,p_t)])
+  for (int i = tid; i < TT * P; i += WIN_THREADS) {
+    const int t = i / P, pp = i % P;
+    const int pt = (t % Tw) / K;
+    const int dy = pt / ws - pp / ws, dx = pt % ws - pp % ws;
+    const float* rk = sRk + ((dy + ws - 1) * (2 * ws - 1) + (dx + ws - 1)) * 32;
+    const float* rq = sRq + ((-dy + ws - 1) * (2 * ws - 1) + (-dx + ws - 1)) * 32;
+    float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll 8
-      for (int d = 0; d < 32; ++d) {
-        a = fmaf(qs[t * 32 + d], rk[d], a);
-        c = fmaf(kT[d * TwP + t], rq[d], c);
-      }
-      QR[i] = a;
-      KR[i] = c;
+    for (int d = 0; d < 32; d += 2) {
+      a0 = fmaf(qT[d * TP + t], rk[d], a0);
+      a1 = fmaf(qT[(d + 1) * TP + t], rk[d + 1], a1);
+      c0 = fmaf(kT[d * TP + t], rq[d], c0);
+      c1 = fmaf(kT[(d + 1) * TP + t], rq[d + 1], c1);
     }
-    __syncthreads();
+    QR[i] = a0 + a1;
+    KR[i] = c0 + c1;
+  }
+  __syncthreads();
 
-    float* myrow = rowbuf + warp * Tw;
-    float* myab = abuf + warp * P;
-    const int nchunk = (Tw + 31) / 32;
-    for (int i = warp; i < Tw; i += WIN_WARPS) {
-      const int pi = i / K;
-      float qreg[32];
+  float* myp = pbuf + warp * Tw * R;
+  float* myab = abuf + warp * P * R;
+  const int groups_per_win = Tw / R;
+  const int ngroups = nw * groups_per_win;
+  for (int g = warp; g < ngroups; g += WIN_WARPS) {
+    const int wl = g / groups_per_win;
+    const int i0 = wl * Tw + (g % groups_per_win) * R;        // first query row (CTA slot index)
+    const int c0 = wl * Tw;                                    // first key column of this window
+    const int* wreg = reg + wl * P;
+    float acc[R][NCH];
 #pragma unroll
-      for (int d = 0; d < 32; d += 4) {
-        const float4 t4 = *reinterpret_cast<const float4*>(qs + i * 32 + d);
-        qreg[d] = t4.x; qreg[d + 1] = t4.y; qreg[d + 2] = t4.z; qreg[d + 3] = t4.w;
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < 32; ++d) {
+      float qv[R], kv[NCH];
+      if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          const float2 t2 = *reinterpret_cast<const float2*>(qT + d * TP + i0 + r);
+          qv[r] = t2.x; qv[r + 1] = t2.y;
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) qv[r] = qT[d * TP + i0 + r];
       }
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int j = c * 32 + lane;
+        kv[c] = (j < Tw) ? kT[d * TP + c0 + j] : 0.f;
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[r][c] = fmaf(qv[r], kv[c], acc[r][c]);
+    }
+    // RPE terms, masks, softmax (row-wise over the window's Tw columns)
+    float inv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = i0 + r, il = i - c0, pi = il / K;
       float m = -INFINITY;
-      for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         const int j = c * 32 + lane;
         float s = -INFINITY;
         if (j < Tw) {
           const int pj = j / K;
-          float acc = 0.f;
-#pragma unroll
-          for (int d = 0; d < 32; ++d) acc = fmaf(qreg[d], kT[d * TwP + j], acc);
-          acc += QR[i * P + pj] + KR[j * P + pi];
-          const bool masked = (reg[pi] != reg[pj]) || (p.self_edge && pi == pj && i != j);
-          s = masked ? -INFINITY : acc;
-          myrow[j] = s;
+          s = acc[r][c] + QR[i * P + pj] + KR[(c0 + j) * P + pi];
+          const bool masked = (wreg[pi] != wreg[pj]) || (p.self_edge && pi == pj && il != j);
+          if (masked) s = -INFINITY;
         }
+        acc[r][c] = s;
         m = fmaxf(m, s);
       }
       m = warp_max(m);
       float sum = 0.f;
-      __syncwarp();
-      for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
         const int j = c * 32 + lane;
-        if (j < Tw) { const float e = expf(myrow[j] - m); myrow[j] = e; sum += e; }
+        if (j < Tw) {
+          const float e = expf(acc[r][c] - m);
+          myp[j * R + r] = e;
+          sum += e;
+        }
       }
-      sum = warp_sum(sum);
-      const float inv = 1.f / sum;
-      __syncwarp();
-      for (int pp = lane; pp < P; pp += 32) {       // per-pixel bucket sums (un-normalised)
-        float a = 0.f;
-        for (int n = 0; n < K; ++n) a += myrow[pp * K + n];
-        myab[pp] = a;
-      }
-      __syncwarp();
-      float o = 0.f;
-      for (int j = 0; j < Tw; ++j) o = fmaf(myrow[j], vs[j * 32 + lane], o);
-      const int yi = pi / ws, xi = pi % ws;
-      for (int pp = 0; pp < P; ++pp) {
-        const int r = (yi - pp / ws + ws - 1) * (2 * ws - 1) + (xi - pp % ws + ws - 1);
-        o = fmaf(myab[pp], sRv[r * 32 + lane], o);
-      }
-      p.out[(size_t)tok_row[i] * kEmbed + head * 32 + lane] = o * inv;
-      __syncwarp();
+      inv[r] = 1.f / warp_sum(sum);
     }
+    __syncwarp();
+    for (int pp = lane; pp < P; pp += 32) {          // per-pixel bucket sums of the un-normalised A
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        float a = 0.f;
+        for (int n = 0; n < K; ++n) a += myp[(pp * K + n) * R + r];
+        myab[pp * R + r] = a;
+      }
+    }
+    __syncwarp();
+    float o[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) o[r] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < Tw; ++j) {
+      const float v = vs[(c0 + j) * 32 + lane];
+      if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int r = 0; r < R; r += 2) {
+          const float2 p2 = *reinterpret_cast<const float2*>(myp + j * R + r);
+          o[r] = fmaf(p2.x, v, o[r]); o[r + 1] = fmaf(p2.y, v, o[r + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) o[r] = fmaf(myp[j * R + r], v, o[r]);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int pi = (i0 + r - c0) / K;
+      const int yi = pi / ws, xi = pi % ws;
+      float acc_rv = o[r];
+      for (int pp = 0; pp < P; ++pp) {
+        const int rr = (yi - pp / ws + ws - 1) * (2 * ws - 1) + (xi - pp % ws + ws - 1);
+        acc_rv = fmaf(myab[pp * R + r], sRv[rr * 32 + lane], acc_rv);
+      }
+      p.out[(size_t)tok_row[i0 + r] * kEmbed + head * 32 + lane] = acc_rv * inv[r];
+    }
+    __syncwarp();
   }
 }
 
@@ -359,6 +422,18 @@ int proposal_attention(const float* qkv, int P, int K, float* out, cudaStream_t 
   return check_launch("proposal_attention");
 }
 
+template <int R, int NCH>
+static int launch_window(const WinParams& p, size_t smem, dim3 grid, cudaStream_t stream) {
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaFuncSetAttribute(window_attention_kernel<R, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  window_attention_kernel<R, NCH><<<grid, WIN_THREADS, smem, stream>>>(p);
+  count_launch();
+  return check_launch("window_attention");
+}
+
 int window_attention(const float* qkv, const float* table, int B, int Hp, int Wp, int K, int ws, int shift,
                      int self_edge, float* out, cudaStream_t stream) {
   NMRF_REQUIRE(qkv && table && out, "window_attention: null pointer");
@@ -368,23 +443,26 @@ int window_attention(const float* qkv, const float* table, int B, int Hp, int Wp
   p.qkv = qkv; p.table = table; p.out = out;
   p.B = B; p.Hp = Hp; p.Wp = Wp; p.K = K; p.ws = ws; p.shift = shift; p.self_edge = self_edge;
   p.nwy = Hp / ws; p.nwx = Wp / ws; p.nwin = B * p.nwy * p.nwx;
-  const int P = ws * ws, Tw = P * K, R = (2 * ws - 1) * (2 * ws - 1);
-  const size_t smem = sizeof(float) * ((size_t)3 * R * 32 + (size_t)2 * Tw * 32 + (size_t)32 * (Tw + 1) + (size_t)2 * Tw * P +
-                                       (size_t)WIN_WARPS * (Tw + P)) + sizeof(int) * (size_t)(Tw + P);
-  NMRF_REQUIRE(smem <= 227 * 1024, "window_attention: ws=%d K=%d needs %zu B of shared memory", ws, K, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
-  // small windows: several windows per CTA so the table staging is amortised and the grid is ~2 waves
+  const int P = ws * ws, Tw = P * K, NR = (2 * ws - 1) * (2 * ws - 1);
+  NMRF_REQUIRE(Tw <= 256, "window_attention: %d tokens per window exceed 256", Tw);
+  const int R = (Tw % 6 == 0) ? 6 : (Tw % 4 == 0) ? 4 : (Tw % 2 == 0) ? 2 : 1;
+  const int nch = (Tw + 31) / 32;
+  // small windows: several windows per CTA so the CTA's 8 warps all have row groups
   int wpc = 1;
-  if (Tw <= 32) wpc = 8; else if (Tw <= 64) wpc = 4;
+  while (wpc < 8 && (wpc * Tw) / R < 2 * WIN_WARPS && 2 * wpc * Tw <= 256) wpc *= 2;
   p.wpc = wpc;
+  const size_t TT = (size_t)wpc * Tw;
+  const size_t smem = sizeof(float) * ((size_t)3 * NR * 32 + (size_t)2 * 32 * (TT + 2) + TT * 32 + 2 * TT * P +
+                                       (size_t)WIN_WARPS * (Tw + P) * R) + sizeof(int) * (TT + (size_t)wpc * P);
+  NMRF_REQUIRE(smem <= 227 * 1024, "window_attention: ws=%d K=%d needs %zu B of shared memory", ws, K, smem);
   dim3 grid((p.nwin + wpc - 1) / wpc, kHeads);
-  window_attention_kernel<<<grid, WIN_THREADS, smem, stream>>>(p);
-  count_launch();
-  return check_launch("window_attention");
+#define NMRF_WIN(RR, NN) if (R == RR && nch <= NN) return launch_window<RR, NN>(p, smem, grid, stream)
+  NMRF_WIN(6, 2); NMRF_WIN(6, 3); NMRF_WIN(6, 4); NMRF_WIN(6, 5);
+  NMRF_WIN(4, 1); NMRF_WIN(4, 2); NMRF_WIN(4, 4);
+  NMRF_WIN(2, 1); NMRF_WIN(2, 2); NMRF_WIN(2, 4); NMRF_WIN(2, 8);
+  NMRF_WIN(6, 8); NMRF_WIN(4, 8);
+#undef NMRF_WIN
+  return launch_window<1, 8>(p, smem, grid, stream);
 }
 
 int stripe_attention(const float* qkv, int B, int h, int w, int K, const float* get_v0, const float* get_v1,

@@ -1,0 +1,321 @@
+// Fused token GEMM on the 5th-generation tensor cores (tcgen05, accumulators in TMEM), exact to fp32
+// level through error-compensated 3xTF32:
+//     x = hi + lo,  hi = rna_tf32(x),  lo = rna_tf32(x - hi);      x.w ~= hi.hi + hi.lo + lo.hi
+// (round-to-nearest splitting is essential: DESIGN.md §3 -- truncation splitting fails the EPE bar).
+// The weights arrive pre-split (W_hi, W_lo: nmrf_split_tf32); the activations are LayerNorm'ed,
+// concatenated and split on the fly by the producer threads while they stage the A operand.
+//
+// Structure (one persistent CTA per SM, 256 threads, 1 CTA/SM because of TMEM):
+//   tile      : 128 token rows x all N (<=512) output columns; fp32 accumulators = N TMEM columns
+//   operands  : K-major, SWIZZLE_128B, BK = 32 fp32 (=128 B) per k-block
+//                 A_hi/A_lo [128 x 32]  double buffered  (2 x 32 KB)   filled by st.shared
+//                 B_hi/B_lo [128 x 32]  double buffered  (2 x 32 KB)   filled by cp.async
+//   schedule  : "units" u = (k-block, n-chunk of 128): all threads fill the unit's buffers, fence to the
+//               async proxy, __syncthreads, then ONE thread issues 12 tcgen05.mma (4 k-steps x 3 products)
+//               and commits to the unit buffer's mbarrier.  The MMAs run asynchronously while all threads
+//               fill the next unit; a buffer is refilled only after the mbarrier of its previous use fired.
+//   epilogue  : tcgen05.ld 32x32b (each warp its TMEM lane quarter) -> bias/act/residual -> global.
+#include "common.cuh"
+
+namespace nmrf {
+namespace {
+
+constexpr int TC_THREADS = 256;
+constexpr int TC_BM = 128;
+constexpr int TC_BN = 128;                 // n-chunk per MMA
+constexpr int TC_BK = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB per operand tile
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
+//   [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4
+//   (= 1024 B between 8-row groups), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format TF32 (=2 at bits 7,10),
+// both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  if (act == 1) return fmaxf(v, 0.f);
+  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  return v;
+}
+
+// byte offset of the 16-byte chunk (row r, chunk c of 8) inside a [rows x 128 B] SWIZZLE_128B tile
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+struct TcSmem {
+  // dynamic shared memory, 1024-byte aligned: A_hi[2] A_lo[2] B_hi[2] B_lo[2] (16 KB each)
+  uint64_t bar[2];          // one per unit buffer (tracks the MMAs that read A[?]/B[buf])
+  uint32_t tmem_base;
+  float mean[TC_BM], rstd[TC_BM];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int ntiles, int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t dsm[];
+  __shared__ TcSmem sm;
+  // carve the operand tiles (the dynamic window is 1024-byte aligned by the launch: see launcher)
+  uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA_hi[2] = {base, base + TC_TILE_BYTES};
+  uint8_t* sA_lo[2] = {base + 2 * TC_TILE_BYTES, base + 3 * TC_TILE_BYTES};
+  uint8_t* sB_hi[2] = {base + 4 * TC_TILE_BYTES, base + 5 * TC_TILE_BYTES};
+  uint8_t* sB_lo[2] = {base + 6 * TC_TILE_BYTES, base + 7 * TC_TILE_BYTES};
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Ktot = a.Kx + a.Ke;
+  const int nkb = (Ktot + TC_BK - 1) / TC_BK;
+  const int nnc = (a.N + TC_BN - 1) / TC_BN;
+  const bool ln = a.ln_gamma != nullptr;
+
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (tid == 0) {
+    mbar_init(&sm.bar[0], 1);
+    mbar_init(&sm.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = sm.tmem_base;
+
+  uint32_t unit = 0;                 // global unit counter of this CTA (buffer = unit & 1, use = unit >> 1)
+
+  // producer mapping for A: thread -> (row = tid/2, 16 consecutive k = 4 chunks of 16 B)
+  const int a_row = tid >> 1, a_c0 = (tid & 1) * 4;
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int row0 = tile * TC_BM;
+    // ---- LayerNorm statistics of the tile's rows (Kx == 128): one warp per 16 rows ----------------
+    if (ln) {
+      for (int i = 0; i < TC_BM / 8; ++i) {
+        const int lr = warp * (TC_BM / 8) + i, r = row0 + lr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < a.rows) v = *reinterpret_cast<const float4*>(a.X + (size_t)r * a.ldx + lane * 4);
+        const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+        const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
+        const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+        if (lane == 0) { sm.mean[lr] = mean; sm.rstd[lr] = 1.f / sqrtf(var + 1e-5f); }
+      }
+      __syncthreads();
+    }
+    const int g_row = row0 + a_row;
+    const bool row_ok = g_row < a.rows;
+    const float* xrow = a.X + (size_t)(row_ok ? g_row : 0) * a.ldx;
+    const float* erow = a.E ? a.E + (size_t)((row_ok ? g_row : 0) / a.ediv) * a.lde : nullptr;
+    const float mean = ln ? sm.mean[a_row] : 0.f, rstd = ln ? sm.rstd[a_row] : 1.f;
+
+    for (int kb = 0; kb < nkb; ++kb) {
+      for (int nc = 0; nc < nnc; ++nc, ++unit) {
+        const int buf = unit & 1;
+        // the MMAs that last read this unit buffer (and, transitively, every earlier MMA -- in particular
+        // all readers of A[kb & 1] two k-blocks ago) must have completed
+        if (unit >= 2) mbar_wait(&sm.bar[buf], ((unit >> 1) - 1) & 1);
+        // ---- B: rows n0.. of W_hi / W_lo, k-block kb, 16-byte cp.async into the swizzled tile --------
+        const int n0 = nc * TC_BN;
+        const int bn = min(TC_BN, a.N - n0);
+        for (int i = tid; i < bn * 8; i += TC_THREADS) {
+          const int r = i >> 3, c = i & 7;
+          const size_t goff = (size_t)(n0 + r) * a.ldw + kb * TC_BK + c * 4;
+          const uint32_t so = swz(r, c);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_hi[buf] + so)), "l"(a.W + goff));
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_lo[buf] + so)), "l"(W_lo + goff));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        // ---- A: produced once per k-block (nc == 0): load, LayerNorm, concat, split hi/lo --------------
+        if (nc == 0) {
+          uint8_t* dh = sA_hi[kb & 1];
+          uint8_t* dl = sA_lo[kb & 1];
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c = a_c0 + cc;
+            const int kk = kb * TC_BK + c * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row_ok && kk < Ktot) {
+              if (kk < a.Kx) {
+                v = *reinterpret_cast<const float4*>(xrow + kk);
+                if (ln) {
+                  const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
+                  const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
+                  v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
+                  v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
+                }
+              } else {
+                v = *reinterpret_cast<const float4*>(erow + (kk - a.Kx));
+              }
+            }
+            float4 h, l;
+            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+            const uint32_t so = swz(a_row, c);
+            *reinterpret_cast<float4*>(dh + so) = h;
+            *reinterpret_cast<float4*>(dl + so) = l;
+          }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        __syncthreads();
+        // ---- MMA issue: one thread, 4 k-steps (8 tf32 = 32 B each) x 3 products -------------------------
+        if (tid == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t idesc = make_idesc(bn);
+          const uint64_t dAh = make_desc(smem_u32(sA_hi[kb & 1])), dAl = make_desc(smem_u32(sA_lo[kb & 1]));
+          const uint64_t dBh = make_desc(smem_u32(sB_hi[buf])), dBl = make_desc(smem_u32(sB_lo[buf]));
+          const uint32_t d = tmem + (uint32_t)n0;
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 8; ++ks) {
+            const uint64_t adv = (uint64_t)(ks * 2);             // +32 bytes (>>4) inside the 128-byte swizzle row
+            umma_tf32(d, dAl + adv, dBh + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(d, dAh + adv, dBl + adv, idesc, 1u);
+            umma_tf32(d, dAh + adv, dBh + adv, idesc, 1u);
+          }
+          umma_commit(&sm.bar[buf]);
+        }
+      }
+    }
+    // ---- wait for the tile's last MMAs, then the epilogue ---------------------------------------------
+    {
+      const uint32_t last = unit - 1;
+      mbar_wait(&sm.bar[last & 1], (last >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      __syncwarp();
+    }
+    {
+      // warp w reads TMEM lanes 32*(w%4)..+32 (its row quarter); warps 0-3 take even 32-column chunks, 4-7 odd
+      const int q = warp & 3, half = warp >> 2;
+      const int r = row0 + q * 32 + lane;
+      const int nchunks = (a.N + 31) / 32;
+      for (int ch = half; ch < nchunks; ch += 2) {
+        float v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        if (r < a.rows) {
+          const int nb = ch * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const int n = nb + j;
+            if (n >= a.N) break;
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (a.bias) {
+              const float4 b = *reinterpret_cast<const float4*>(a.bias + n);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            o.x = act_fn(o.x, a.act); o.y = act_fn(o.y, a.act); o.z = act_fn(o.z, a.act); o.w = act_fn(o.w, a.act);
+            if (a.R) {
+              const float4 rr = *reinterpret_cast<const float4*>(a.R + (size_t)r * a.ldr + n);
+              o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+            }
+            *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
+          }
+        }
+      }
+    }
+    // TMEM (and the LN statistics) are reused by the next tile
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(tmem_cols));
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i];
+  const float h = rna_tf32(x);
+  hi[i] = h;
+  lo[i] = rna_tf32(x - h);
+}
+
+}  // namespace
+
+// W = W_hi, W_lo pre-split; ldw must be a multiple of 32 and cover Kx+Ke rounded up to 32 (zero padded)
+int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream) {
+  static int num_sms = 0;
+  static bool configured = false;
+  const size_t dyn = 8 * TC_TILE_BYTES + 1024;
+  if (!configured) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(token_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    configured = true;
+  }
+  const int ntiles = (a.rows + TC_BM - 1) / TC_BM;
+  int cols = 32;
+  while (cols < a.N) cols <<= 1;
+  const int grid = ntiles < num_sms ? ntiles : num_sms;
+  token_gemm_tc_kernel<<<grid, TC_THREADS, dyn, stream>>>(a, W_lo, ntiles, cols);
+  count_launch();
+  return check_launch("token_gemm_tc");
+}
+
+int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream) {
+  NMRF_REQUIRE(w && hi && lo && n >= 0, "split_tf32: bad arguments");
+  if (n == 0) return NMRF_OK;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, hi, lo, n);
+  count_launch();
+  return check_launch("split_tf32");
+}
+
+}  // namespace nmrf

@@ -19,6 +19,11 @@ from ._lib import GemmArgs, SeedWeights, lib
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 
+def _use_tc_default():
+    import os
+    return os.environ.get("NMRF_B200_GEMM", "tc").lower() != "simt"
+
+
 @dataclass
 class HotPathConfig:
     """The hyper-parameters the kernels need (nmrf/config/default.py:37-61)."""
@@ -31,6 +36,7 @@ class HotPathConfig:
     num_infer_layers: int = 5
     num_refine_layers: int = 5
     eps: float = 1e-3                      # DPN.py:51
+    tensor_cores: bool = True              # tcgen05 3xTF32 GEMMs (False / NMRF_B200_GEMM=simt: exact-fp32 FMA kernel)
 
 
 def _f32(t):
@@ -125,6 +131,8 @@ class _Launches:
         self.calls = []
         self.cost = []          # algorithmic (flops, HBM bytes) per launch, for the roofline report
         self._keep = []
+        self._splits = {}
+        self.tensor_cores = False
 
     def add(self, fn, what, *args, flops=0.0, bytes=0.0):
         self.calls.append((fn, what, args))
@@ -133,7 +141,24 @@ class _Launches:
     def keep(self, *objs):
         self._keep.extend(objs)
 
+    def split(self, W):
+        """(hi, lo) = nmrf_split_tf32 of an [N, K] weight, K zero-padded to a multiple of 32; cached per tensor"""
+        key = W.data_ptr()
+        if key not in self._splits:
+            N, K = W.shape
+            Kp = (K + 31) // 32 * 32
+            Wp = W if Kp == K else torch.nn.functional.pad(W, (0, Kp - K))
+            Wp = Wp.contiguous()
+            hi, lo = torch.empty_like(Wp), torch.empty_like(Wp)
+            _lib.check(lib.nmrf_split_tf32(Wp.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wp.numel(),
+                                           torch.cuda.current_stream().cuda_stream), "split_tf32")
+            self._splits[key] = (hi, lo, W)
+        return self._splits[key][:2]
+
     def gemm(self, what, X, W, Y, rows, N, *, Kx=None, E=None, Ke=0, ediv=1, ln=None, bias=None, R=None, act=ACT_NONE):
+        W_lo = None
+        if self.tensor_cores and N % 16 == 0 and N <= 512 and W.is_cuda:
+            W, W_lo = self.split(W)
         a = GemmArgs()
         a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), (Kx if Kx is not None else X.shape[1])
         a.E, a.lde, a.Ke, a.ediv = (E.data_ptr() if E is not None else None), (E.stride(0) if E is not None else 0), Ke, ediv
@@ -143,7 +168,8 @@ class _Launches:
         a.R, a.ldr = (R.data_ptr(), R.stride(0)) if R is not None else (None, 0)
         a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
         a.rows, a.N, a.act = rows, N, act
-        self.keep(a, X, W, Y, E, ln, bias, R)
+        a.W_lo = W_lo.data_ptr() if W_lo is not None else None
+        self.keep(a, X, W, W_lo, Y, E, ln, bias, R)
         # algorithmic work: 2*MAC flops; activations read+written once (weights are L2-resident, excluded)
         flops = 2.0 * rows * N * (a.Kx + Ke)
         nbytes = 4.0 * (rows * a.Kx + (rows // max(ediv, 1)) * Ke + rows * N * (2 if R is not None else 1))
@@ -217,6 +243,7 @@ class HotPathPlan:
         self.delta, self.score = new(Tmax, 64), new(Tmax, 64)
         self.pw = pw
         self.launches = _Launches()
+        self.launches.tensor_cores = bool(cfg.tensor_cores) and _use_tc_default()
         self._build(pw)
 
     # -------------------------------------------------------------------------------------------
@@ -312,6 +339,36 @@ class HotPathPlan:
     def run(self):
         """Launch the whole hot path on the current stream (inputs already copied in)."""
         self.launches.run(torch.cuda.current_stream().cuda_stream)
+
+    def run_with_taps(self):
+        """Eager run that clones the stage-boundary tensors (same names as the oracle's taps).  Debug /
+        parity tooling only: allocates."""
+        stream = torch.cuda.current_stream().cuda_stream
+        g, taps = self.geom, {}
+        K = g["K"]
+        for fn, what, args in self.launches.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, what)
+            if what == "cost_volume_topk":
+                taps.update(cost_volume=self.cost_volume.clone(), prob=self.prob.clone(), seeds=self.seeds.clone())
+            elif what == "propagation.proj":
+                taps["prop_embed"] = self.x[:g["T8"]].reshape(-1, K, 128).clone()
+            elif what.startswith("prop") and what.endswith(".fc2") and what[4].isdigit():
+                taps[f"prop_layer{what[4:-4]}"] = self.x[:g["T8"]].reshape(-1, K, 128).clone()
+            elif what == "prop_head.2":
+                taps["labels"] = self.labels.clone()
+            elif what.startswith("inference") and what.endswith(".fc2") and what[9].isdigit():
+                taps[f"inference_layer{what[9:-4]}"] = self.x[:g["T8p"]].reshape(-1, K, 128).clone()
+            elif what.startswith("refinement") and what.endswith(".fc2") and what[10].isdigit():
+                taps[f"refinement_layer{what[10:-4]}"] = self.x[:g["T4p"]].reshape(-1, 1, 128).clone()
+            elif what == "infer_score_head":
+                taps.update(delta=self.delta[:g["T8p"]].clone(), score=self.score[:g["T8p"]].clone())
+            elif what == "select_median":
+                taps["disp_curr"] = self.disp_curr.clone()
+            elif what == "refine_tail":
+                taps.update(disp=self.disp.clone(), disp_pred=self.disp_pred.clone())
+        return taps
 
     @property
     def num_launches(self):

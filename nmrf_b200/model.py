@@ -205,6 +205,7 @@ class NMRF(nn.Module):
         init_like_reference(self)
         self._packed = None
         self._plans = {}
+        self.cudnn_benchmark = False      # let cuDNN autotune the (out-of-path) fp32 convolutions
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -263,19 +264,22 @@ class NMRF(nn.Module):
             img2 = F.pad(img2, [0, pad_w, 0, pad_h], mode="replicate")
         img1 = img1.contiguous(memory_format=torch.channels_last)
         img2 = img2.contiguous(memory_format=torch.channels_last)
-        f1, f2 = self.extract_feature(img1, img2)                  # [1/8, 1/4]
-        C, h8, w8 = f1[0].shape[1:]
-        plan = self.plan_for(B, C, h8, w8, H, W)
-        nhwc = lambda t: t.permute(0, 2, 3, 1)
-        plan.f1_8.copy_(nhwc(f1[0]))
-        plan.f2_8.copy_(nhwc(f2[0]))
-        plan.context.copy_(nhwc(self.dpn.proj(f1[0])))
-        for s, (cc, gw) in enumerate(((plan.cc8, plan.gw8), (plan.cc4, plan.gw4))):
-            both = torch.cat((f1[s], f2[s]), 0)                    # InstanceNorm is per-sample: batching is exact
-            c = nhwc(self.concatconv(both))
-            g = nhwc(self.gw(both))
-            cc[0].copy_(c[:B]); cc[1].copy_(c[B:])
-            gw[0].copy_(g[:B]); gw[1].copy_(g[B:])
+        # exact-fp32 convolutions: cuDNN's default TF32 moves the features by ~5e-4 relative, which flips
+        # top-K / argmax decisions downstream (EPE 0.2-0.4 px measured) -- same reason as DESIGN.md §3
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.cudnn_benchmark, allow_tf32=False):
+            f1, f2 = self.extract_feature(img1, img2)                  # [1/8, 1/4]
+            C, h8, w8 = f1[0].shape[1:]
+            plan = self.plan_for(B, C, h8, w8, H, W)
+            nhwc = lambda t: t.permute(0, 2, 3, 1)
+            plan.f1_8.copy_(nhwc(f1[0]))
+            plan.f2_8.copy_(nhwc(f2[0]))
+            plan.context.copy_(nhwc(self.dpn.proj(f1[0])))
+            for s, (cc, gw) in enumerate(((plan.cc8, plan.gw8), (plan.cc4, plan.gw4))):
+                both = torch.cat((f1[s], f2[s]), 0)                    # InstanceNorm is per-sample: batching is exact
+                c = nhwc(self.concatconv(both))
+                g = nhwc(self.gw(both))
+                cc[0].copy_(c[:B]); cc[1].copy_(c[B:])
+                gw[0].copy_(g[:B]); gw[1].copy_(g[B:])
         plan.run()
         K = self.num_proposals
         return {

@@ -32,9 +32,22 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None):
-    """Y = act(concat(LN?(X), E[r // ediv]) @ W.T + bias) (+ R).  X [rows,Kx], E [*,Ke], W [N,>=Kx+Ke]."""
-    for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R)):
+def split_tf32(W):
+    """(hi, lo) with hi = rna_tf32(W), lo = rna_tf32(W - hi); the input dimension is zero-padded to a
+    multiple of 32 as the tensor-core GEMM requires."""
+    _chk(W, "W")
+    N, K = W.shape
+    Kp = (K + 31) // 32 * 32
+    Wp = (W if Kp == K else torch.nn.functional.pad(W, (0, Kp - K))).contiguous()
+    hi, lo = torch.empty_like(Wp), torch.empty_like(Wp)
+    _lib.check(lib.nmrf_split_tf32(Wp.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wp.numel(), _stream()), "split_tf32")
+    return hi, lo
+
+
+def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, W_lo=None):
+    """Y = act(concat(LN?(X), E[r // ediv]) @ W.T + bias) (+ R).  X [rows,Kx], E [*,Ke], W [N,>=Kx+Ke].
+    With W_lo (and W = hi part, both from split_tf32) the tcgen05 3xTF32 kernel is used."""
+    for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R), ("W_lo", W_lo)):
         _chk(t, n)
     rows, Kx = X.shape
     N = W.shape[0]
@@ -48,6 +61,7 @@ def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=N
     a.R, a.ldr = _p(R), (R.stride(0) if R is not None else 0)
     a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
     a.rows, a.N, a.act = rows, N, act
+    a.W_lo = _p(W_lo)
     _lib.check(lib.nmrf_token_gemm(ctypes.byref(a), _stream()), "token_gemm")
     return Y
 

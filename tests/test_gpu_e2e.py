@@ -20,7 +20,7 @@ def _seed_mismatch_is_tie(out_seeds, ref_seeds, prob_nms, K):
     a = out_seeds.long().reshape(-1, K).cpu()
     b = ref_seeds.long().reshape(-1, K)
     va, vb = prob_nms.gather(1, a), prob_nms.gather(1, b)
-    assert float((va - vb).abs().max()) <= 1e-6
+    assert float((va - vb).abs().max()) <= 2e-6
     return float((a != b).any(-1).float().mean())
 
 
@@ -103,7 +103,7 @@ def test_stage_chain_with_stress_weights():
         x = ops.token_gemm(att, wt["proj_w"], bias=wt["proj_b"], R=x)
         hid = ops.token_gemm(x, wt["fc1_w"], ln=wt["n2"], bias=wt["fc1_b"], act=2)
         x = ops.token_gemm(hid, wt["fc2_w"], bias=wt["fc2_b"], R=x)
-        assert rel(x, taps[f"inference_layer{i}"]) <= 2e-4, f"inference layer {i}"
+        assert rel(x.reshape(-1, K, 128), taps[f"inference_layer{i}"]) <= 2e-4, f"inference layer {i}"
 
 
 def test_full_size_properties():

@@ -75,10 +75,11 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
   const int P = ws * ws, Tw = P * K, NR = (2 * ws - 1) * (2 * ws - 1);
   const int TT = p.wpc * Tw;           // token slots of all windows of this CTA
   const int TP = TT + 2;               // even row stride: 8-byte aligned float2 broadcasts, conflict-free columns
-  float* sRq = smem;                   // [NR][32]  (pre-scaled)
-  float* sRk = sRq + NR * 32;          // [NR][32]
-  float* sRv = sRk + NR * 32;          // [NR][32]
-  float* qT = sRv + NR * 32;           // [32][TP]  (pre-scaled)
+  constexpr int RS = 33;               // table row stride: rows are read by lanes at a fixed d -> odd stride, no bank conflicts
+  float* sRq = smem;                   // [NR][33]  (pre-scaled)
+  float* sRk = sRq + NR * RS;          // [NR][33]
+  float* sRv = sRk + NR * RS;          // [NR][33]
+  float* qT = sRv + NR * RS + (NR & 1);   // [32][TP]  (pre-scaled); keep 8-byte alignment
   float* kT = qT + 32 * TP;            // [32][TP]
   float* vs = kT + 32 * TP;            // [TT][32]
   float* QR = vs + TT * 32;            // [TT][P]
@@ -96,9 +97,9 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
   for (int i = tid; i < NR * 32; i += WIN_THREADS) {
     const int r = i >> 5, d = i & 31;
     const float* row = p.table + (size_t)r * kQkv + head * 96;
-    sRq[i] = row[d] * kScale;
-    sRk[i] = row[32 + d];
-    sRv[i] = row[64 + d];
+    sRq[r * RS + d] = row[d] * kScale;
+    sRk[r * RS + d] = row[32 + d];
+    sRv[r * RS + d] = row[64 + d];
   }
   for (int t = tid; t < TT; t += WIN_THREADS) {
     const int wl = t / Tw, tl = t % Tw;
@@ -138,8 +139,8 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
     const int t = i / P, pp = i % P;
     const int pt = (t % Tw) / K;
     const int dy = pt / ws - pp / ws, dx = pt % ws - pp % ws;
-    const float* rk = sRk + ((dy + ws - 1) * (2 * ws - 1) + (dx + ws - 1)) * 32;
-    const float* rq = sRq + ((-dy + ws - 1) * (2 * ws - 1) + (-dx + ws - 1)) * 32;
+    const float* rk = sRk + ((dy + ws - 1) * (2 * ws - 1) + (dx + ws - 1)) * RS;
+    const float* rq = sRq + ((-dy + ws - 1) * (2 * ws - 1) + (-dx + ws - 1)) * RS;
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll 8
     for (int d = 0; d < 32; d += 2) {
@@ -256,7 +257,7 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
       float acc_rv = o[r];
       for (int pp = 0; pp < P; ++pp) {
         const int rr = (yi - pp / ws + ws - 1) * (2 * ws - 1) + (xi - pp % ws + ws - 1);
-        acc_rv = fmaf(myab[pp * R + r], sRv[rr * 32 + lane], acc_rv);
+        acc_rv = fmaf(myab[pp * R + r], sRv[rr * 33 + lane], acc_rv);
       }
       p.out[(size_t)tok_row[i0 + r] * kEmbed + head * 32 + lane] = acc_rv * inv[r];
     }
@@ -452,7 +453,7 @@ int window_attention(const float* qkv, const float* table, int B, int Hp, int Wp
   while (wpc < 8 && (wpc * Tw) / R < 2 * WIN_WARPS && 2 * wpc * Tw <= 256) wpc *= 2;
   p.wpc = wpc;
   const size_t TT = (size_t)wpc * Tw;
-  const size_t smem = sizeof(float) * ((size_t)3 * NR * 32 + (size_t)2 * 32 * (TT + 2) + TT * 32 + 2 * TT * P +
+  const size_t smem = sizeof(float) * ((size_t)3 * NR * 33 + (NR & 1) + (size_t)2 * 32 * (TT + 2) + TT * 32 + 2 * TT * P +
                                        (size_t)WIN_WARPS * (Tw + P) * R) + sizeof(int) * (TT + (size_t)wpc * P);
   NMRF_REQUIRE(smem <= 227 * 1024, "window_attention: ws=%d K=%d needs %zu B of shared memory", ws, K, smem);
   dim3 grid((p.nwin + wpc - 1) / wpc, kHeads);

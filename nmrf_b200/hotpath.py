@@ -307,8 +307,9 @@ class HotPathPlan:
         nrm = pw.stacks["refinement"]["norm"]
         L_.gemm("refine_head.0", self.x, w0, self.h1, T4p, 128, ln=nrm, bias=b0, act=ACT_RELU)
         L_.gemm("refine_head.1", self.h1, w1, self.h2, T4p, 128, bias=b1, act=ACT_RELU)
-        L_.gemm("refine_head.2", self.h2, w2, self.delta, T4p, 16, bias=b2)
-        L_.add(lib.nmrf_refine_tail, "refine_tail", ptr(self.delta), ptr(self.disp_curr), B, h4, w4, g["Hp4"], g["Wp4"],
+        delta16 = self.delta.view(-1)[:T4p * 16].view(T4p, 16)      # dense [T4p,16] as nmrf_refine_tail expects
+        L_.gemm("refine_head.2", self.h2, w2, delta16, T4p, 16, bias=b2)
+        L_.add(lib.nmrf_refine_tail, "refine_tail", ptr(delta16), ptr(self.disp_curr), B, h4, w4, g["Hp4"], g["Wp4"],
                g["top4"], g["left4"], self.H, self.W, ptr(self.disp_pred), ptr(self.disp))
 
     def _stack(self, L_, S, name, labels, cc, gw, h, w, K, Hp, Wp, top, left, ws, normalizer, with_self):

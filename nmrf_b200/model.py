@@ -12,6 +12,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .exactconv import ExactConvCache, patch_convs
 from .hotpath import HotPathConfig, HotPathPlan, PackedWeights
 
 
@@ -206,6 +207,10 @@ class NMRF(nn.Module):
         self._packed = None
         self._plans = {}
         self.cudnn_benchmark = False      # let cuDNN autotune the (out-of-path) fp32 convolutions
+        # out-of-path torch convolutions: "3xtf32" = fp32-accurate on TF32 tensor cores (exactconv.py),
+        # "fp32" = cuDNN with TF32 disabled (slow on B200), "tf32" = cuDNN default (fast, breaks parity)
+        self.conv_mode = "3xtf32"
+        self._conv_cache = ExactConvCache()
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -217,6 +222,8 @@ class NMRF(nn.Module):
         """Drop packed weights and launch plans (call after changing parameters in place)."""
         self._packed = None
         self._plans = {}
+        if hasattr(self, "_conv_cache"):
+            self._conv_cache.clear()
 
     def _apply(self, fn, *a, **k):
         self.invalidate()
@@ -266,7 +273,11 @@ class NMRF(nn.Module):
         img2 = img2.contiguous(memory_format=torch.channels_last)
         # exact-fp32 convolutions: cuDNN's default TF32 moves the features by ~5e-4 relative, which flips
         # top-K / argmax decisions downstream (EPE 0.2-0.4 px measured) -- same reason as DESIGN.md §3
-        with torch.backends.cudnn.flags(enabled=True, benchmark=self.cudnn_benchmark, allow_tf32=False):
+        self._conv_cache.enabled = self.conv_mode == "3xtf32"
+        if self._conv_cache.enabled:
+            for m in (self.backbone if self.compat else self.image_encoder, self.concatconv, self.gw, self.dpn.proj):
+                patch_convs(m, self._conv_cache)
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.cudnn_benchmark, allow_tf32=(self.conv_mode == "tf32")):
             f1, f2 = self.extract_feature(img1, img2)                  # [1/8, 1/4]
             C, h8, w8 = f1[0].shape[1:]
             plan = self.plan_for(B, C, h8, w8, H, W)

@@ -9,11 +9,12 @@
 //   tile      : 128 token rows x all N (<=512) output columns; fp32 accumulators = N TMEM columns
 //   operands  : K-major, SWIZZLE_128B, BK = 32 fp32 (=128 B) per k-block
 //                 A_hi/A_lo [128 x 32]  double buffered  (2 x 32 KB)   filled by st.shared
-//                 B_hi/B_lo [128 x 32]  double buffered  (2 x 32 KB)   filled by cp.async
-//   schedule  : "units" u = (k-block, n-chunk of 128): all threads fill the unit's buffers, fence to the
-//               async proxy, __syncthreads, then ONE thread issues 12 tcgen05.mma (4 k-steps x 3 products)
-//               and commits to the unit buffer's mbarrier.  The MMAs run asynchronously while all threads
-//               fill the next unit; a buffer is refilled only after the mbarrier of its previous use fired.
+//                 B_hi/B_lo [128 x 32]  triple buffered  (3 x 32 KB)   filled by cp.async, one unit ahead
+//   schedule  : "units" u = (k-block, n-chunk of 128).  Iteration u: wait for the MMAs of unit u-2 (frees the
+//               B buffer of unit u+1 and the A buffer about to be rewritten), start the cp.async of B(u+1),
+//               produce A if the k-block changed, wait for B(u), fence to the async proxy, __syncthreads, then
+//               ONE thread issues 12 tcgen05.mma (4 k-steps x 3 products) and commits to the unit's mbarrier.
+//               MMA(u) is issued while MMA(u-1) is still running; the weight prefetch runs across tiles.
 //   epilogue  : tcgen05.ld 32x32b (each warp its TMEM lane quarter) -> bias/act/residual -> global.
 #include "common.cuh"
 
@@ -99,9 +100,10 @@ __device__ __forceinline__ float act_fn(float v, int act) {
 // byte offset of the 16-byte chunk (row r, chunk c of 8) inside a [rows x 128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
+constexpr int TC_NB = 3;    // B buffers
 struct TcSmem {
-  // dynamic shared memory, 1024-byte aligned: A_hi[2] A_lo[2] B_hi[2] B_lo[2] (16 KB each)
-  uint64_t bar[2];          // one per unit buffer (tracks the MMAs that read A[?]/B[buf])
+  // dynamic shared memory, 1024-byte aligned: A_hi[2] A_lo[2] B_hi[3] B_lo[3] (16 KB each)
+  uint64_t bar[TC_NB];      // one per B buffer: completion of the MMAs of the unit that used it
   uint32_t tmem_base;
   float mean[TC_BM], rstd[TC_BM];
 };
@@ -114,8 +116,8 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
   uint8_t* sA_hi[2] = {base, base + TC_TILE_BYTES};
   uint8_t* sA_lo[2] = {base + 2 * TC_TILE_BYTES, base + 3 * TC_TILE_BYTES};
-  uint8_t* sB_hi[2] = {base + 4 * TC_TILE_BYTES, base + 5 * TC_TILE_BYTES};
-  uint8_t* sB_lo[2] = {base + 6 * TC_TILE_BYTES, base + 7 * TC_TILE_BYTES};
+  uint8_t* sB_hi[TC_NB] = {base + 4 * TC_TILE_BYTES, base + 5 * TC_TILE_BYTES, base + 6 * TC_TILE_BYTES};
+  uint8_t* sB_lo[TC_NB] = {base + 7 * TC_TILE_BYTES, base + 8 * TC_TILE_BYTES, base + 9 * TC_TILE_BYTES};
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ktot = a.Kx + a.Ke;
@@ -128,8 +130,7 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    mbar_init(&sm.bar[0], 1);
-    mbar_init(&sm.bar[1], 1);
+    for (int i = 0; i < TC_NB; ++i) mbar_init(&sm.bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -137,13 +138,31 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
 
-  uint32_t unit = 0;                 // global unit counter of this CTA (buffer = unit & 1, use = unit >> 1)
+  uint32_t unit = 0;                 // global unit counter of this CTA (B buffer = unit % 3, use = unit / 3)
+  const int upt = nkb * nnc;         // units per tile
 
   // producer mapping for A: thread -> (row = tid/2, 16 consecutive k = 4 chunks of 16 B)
   const int a_row = tid >> 1, a_c0 = (tid & 1) * 4;
 
+  // B tile of local unit `ut` (k-block ut / nnc, n-chunk ut % nnc) -> buffer b; 16-byte cp.async, swizzled
+  auto load_B = [&](int ut, int b) {
+    const int kb = ut / nnc, n0 = (ut % nnc) * TC_BN;
+    const int bn = min(TC_BN, a.N - n0);
+    for (int i = tid; i < bn * 8; i += TC_THREADS) {
+      const int r = i >> 3, c = i & 7;
+      const size_t goff = (size_t)(n0 + r) * a.ldw + kb * TC_BK + c * 4;
+      const uint32_t so = swz(r, c);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_hi[b] + so)), "l"(a.W + goff));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_lo[b] + so)), "l"(W_lo + goff));
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (blockIdx.x < ntiles) load_B(0, 0);        // prologue: the first unit's weights
+
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int row0 = tile * TC_BM;
+    const bool has_next_tile = tile + (int)gridDim.x < ntiles;
     // ---- LayerNorm statistics of the tile's rows (Kx == 128): one warp per 16 rows ----------------
     if (ln) {
       for (int i = 0; i < TC_BM / 8; ++i) {
@@ -163,78 +182,81 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
     const float* erow = a.E ? a.E + (size_t)((row_ok ? g_row : 0) / a.ediv) * a.lde : nullptr;
     const float mean = ln ? sm.mean[a_row] : 0.f, rstd = ln ? sm.rstd[a_row] : 1.f;
 
-    for (int kb = 0; kb < nkb; ++kb) {
-      for (int nc = 0; nc < nnc; ++nc, ++unit) {
-        const int buf = unit & 1;
-        // the MMAs that last read this unit buffer (and, transitively, every earlier MMA -- in particular
-        // all readers of A[kb & 1] two k-blocks ago) must have completed
-        if (unit >= 2) mbar_wait(&sm.bar[buf], ((unit >> 1) - 1) & 1);
-        // ---- B: rows n0.. of W_hi / W_lo, k-block kb, 16-byte cp.async into the swizzled tile --------
+    // raw (pre-LayerNorm) A values of one k-block for this thread: 4 chunks of 4 floats, fetched one k-block ahead
+    float4 araw[4];
+    auto fetch_A = [&](int kb) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int kk = kb * TC_BK + (a_c0 + cc) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row_ok && kk < Ktot) v = (kk < a.Kx) ? *reinterpret_cast<const float4*>(xrow + kk)
+                                                 : *reinterpret_cast<const float4*>(erow + (kk - a.Kx));
+        araw[cc] = v;
+      }
+    };
+    fetch_A(0);
+
+    for (int ut = 0; ut < upt; ++ut, ++unit) {
+      const int kb = ut / nnc, nc = ut % nnc;
+      const int buf = unit % TC_NB;
+      // MMAs of unit-2 (hence of every earlier unit) complete: frees B[(unit+1)%3] and the A buffer of k-block kb-2.
+      // (unit-2 is the newest unit whose barrier phase is unambiguous: its buffer is next used by unit+1.)
+      if (unit >= 2) mbar_wait(&sm.bar[(unit - 2) % TC_NB], ((unit - 2) / TC_NB) & 1);
+      // ---- prefetch the next unit's weights (next tile starts again at k-block 0, n-chunk 0) ----------------
+      const bool prefetch = (ut + 1 < upt) || has_next_tile;
+      if (prefetch) load_B((ut + 1 < upt) ? ut + 1 : 0, (unit + 1) % TC_NB);
+      // ---- A: produced once per k-block (nc == 0): load, LayerNorm, concat, split hi/lo ---------------------
+      if (nc == 0) {
+        uint8_t* dh = sA_hi[kb & 1];
+        uint8_t* dl = sA_lo[kb & 1];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c = a_c0 + cc;
+          const int kk = kb * TC_BK + c * 4;
+          float4 v = araw[cc];
+          if (ln && row_ok && kk < a.Kx) {
+            const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
+            const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
+            v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
+            v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
+          }
+          float4 h, l;
+          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+          l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+          const uint32_t so = swz(a_row, c);
+          *reinterpret_cast<float4*>(dh + so) = h;
+          *reinterpret_cast<float4*>(dl + so) = l;
+        }
+        if (kb + 1 < nkb) fetch_A(kb + 1);      // in flight while this k-block's MMAs run
+      }
+      // B(unit) has landed (only the group just committed for unit+1 may still be in flight)
+      if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+      __syncthreads();
+      // ---- MMA issue: one thread, 4 k-steps (8 tf32 = 32 B each) x 3 products -----------------------------------
+      if (tid == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int n0 = nc * TC_BN;
         const int bn = min(TC_BN, a.N - n0);
-        for (int i = tid; i < bn * 8; i += TC_THREADS) {
-          const int r = i >> 3, c = i & 7;
-          const size_t goff = (size_t)(n0 + r) * a.ldw + kb * TC_BK + c * 4;
-          const uint32_t so = swz(r, c);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_hi[buf] + so)), "l"(a.W + goff));
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_lo[buf] + so)), "l"(W_lo + goff));
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        // ---- A: produced once per k-block (nc == 0): load, LayerNorm, concat, split hi/lo --------------
-        if (nc == 0) {
-          uint8_t* dh = sA_hi[kb & 1];
-          uint8_t* dl = sA_lo[kb & 1];
+        const uint32_t idesc = make_idesc(bn);
+        const uint64_t dAh = make_desc(smem_u32(sA_hi[kb & 1])), dAl = make_desc(smem_u32(sA_lo[kb & 1]));
+        const uint64_t dBh = make_desc(smem_u32(sB_hi[buf])), dBl = make_desc(smem_u32(sB_lo[buf]));
+        const uint32_t d = tmem + (uint32_t)n0;
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const int c = a_c0 + cc;
-            const int kk = kb * TC_BK + c * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (row_ok && kk < Ktot) {
-              if (kk < a.Kx) {
-                v = *reinterpret_cast<const float4*>(xrow + kk);
-                if (ln) {
-                  const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
-                  const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
-                  v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
-                  v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
-                }
-              } else {
-                v = *reinterpret_cast<const float4*>(erow + (kk - a.Kx));
-              }
-            }
-            float4 h, l;
-            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-            const uint32_t so = swz(a_row, c);
-            *reinterpret_cast<float4*>(dh + so) = h;
-            *reinterpret_cast<float4*>(dl + so) = l;
-          }
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 2);             // +32 bytes (>>4) inside the 128-byte swizzle row
+          umma_tf32(d, dAl + adv, dBh + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+          umma_tf32(d, dAh + adv, dBl + adv, idesc, 1u);
+          umma_tf32(d, dAh + adv, dBh + adv, idesc, 1u);
         }
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-        __syncthreads();
-        // ---- MMA issue: one thread, 4 k-steps (8 tf32 = 32 B each) x 3 products -------------------------
-        if (tid == 0) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t idesc = make_idesc(bn);
-          const uint64_t dAh = make_desc(smem_u32(sA_hi[kb & 1])), dAl = make_desc(smem_u32(sA_lo[kb & 1]));
-          const uint64_t dBh = make_desc(smem_u32(sB_hi[buf])), dBl = make_desc(smem_u32(sB_lo[buf]));
-          const uint32_t d = tmem + (uint32_t)n0;
-#pragma unroll
-          for (int ks = 0; ks < TC_BK / 8; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);             // +32 bytes (>>4) inside the 128-byte swizzle row
-            umma_tf32(d, dAl + adv, dBh + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(d, dAh + adv, dBl + adv, idesc, 1u);
-            umma_tf32(d, dAh + adv, dBh + adv, idesc, 1u);
-          }
-          umma_commit(&sm.bar[buf]);
-        }
+        umma_commit(&sm.bar[buf]);
       }
     }
     // ---- wait for the tile's last MMAs, then the epilogue ---------------------------------------------
     {
       const uint32_t last = unit - 1;
-      mbar_wait(&sm.bar[last & 1], (last >> 1) & 1);
+      mbar_wait(&sm.bar[last % TC_NB], (last / TC_NB) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __syncwarp();
     }
@@ -293,7 +315,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
 int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream) {
   static int num_sms = 0;
   static bool configured = false;
-  const size_t dyn = 8 * TC_TILE_BYTES + 1024;
+  const size_t dyn = 10 * TC_TILE_BYTES + 1024;
   if (!configured) {
     int dev = 0;
     cudaGetDevice(&dev);

@@ -80,8 +80,6 @@ def parity_metrics(model, sd, max_disp, K, L, img1, img2):
     m["labels_abs_err_max_same_seed"] = float((taps["labels"] - ot["labels"]).abs()[same_seed].max())
     for i in range(int(L[1])):
         m["rel_err"][f"inference_layer{i}"] = rel(taps[f"inference_layer{i}"], ot[f"inference_layer{i}"])
-    for i in range(int(L[2])):
-        m["rel_err"][f"refinement_layer{i}"] = rel(taps[f"refinement_layer{i}"], ot[f"refinement_layer{i}"])
     Hp8, Wp8, top, left = g["Hp8"], g["Wp8"], g["top8"], g["left8"]
     sc = taps["score"].reshape(B, Hp8, Wp8, K, 64)[:, top:top + h8, left:left + w8]
     sc = sc.reshape(B, h8, w8, K, 8, 8).permute(0, 1, 4, 2, 5, 3).reshape(B, h8 * 8, w8 * 8, K)
@@ -98,6 +96,12 @@ def parity_metrics(model, sd, max_disp, K, L, img1, img2):
     # 6x6-window inference attention, its 1/8-res neighbourhood: exclude +-6 blocks (24 px) around every flip
     bad = F.max_pool2d((~blk).float()[:, None], 13, 1, 6)[:, 0] > 0
     clean = (~bad).repeat_interleave(4, 1).repeat_interleave(4, 2)[:, :H, :W]
+    # refinement tokens (padded 1/4 grid) compared away from flips only: next to a flip they legitimately differ
+    Hp4, Wp4, t4, l4 = g["Hp4"], g["Wp4"], g["top4"], g["left4"]
+    for i in range(int(L[2])):
+        a = taps[f"refinement_layer{i}"].reshape(B, Hp4, Wp4, 128)[:, t4:t4 + 2 * h8, l4:l4 + 2 * w8]
+        b = ot[f"refinement_layer{i}"].reshape(B, Hp4, Wp4, 128)[:, t4:t4 + 2 * h8, l4:l4 + 2 * w8]
+        m["rel_err"][f"refinement_layer{i}"] = rel(a[~bad], b[~bad]) if (~bad).any() else 0.0
     m["EPE"] = float(d.mean())
     m["max_err_px"] = float(d.max())
     m["frac_px_err_gt_1e-3"] = float((d > 1e-3).float().mean())

@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
   float* abuf = pbuf + WIN_WARPS * Tw * R;   // [WARPS][P][R]  per-pixel bucket sums
   int* tok_row = reinterpret_cast<int*>(abuf + WIN_WARPS * P * R);   // [TT] global token row
   int* reg = tok_row + TT;             // [wpc*P] Swin region id (rolled coordinates)
+  int* pixof = reg + p.wpc * P;        // [Tw]   pixel of a window-local token slot (t / K) -- no divisions in the hot loops
+  int* relof = pixof + Tw;             // [P*P]  relative-position row (x33) of the pixel pair (pi, pj)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int head = blockIdx.y;
@@ -100,6 +102,11 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
     sRq[r * RS + d] = row[d] * kScale;
     sRk[r * RS + d] = row[32 + d];
     sRv[r * RS + d] = row[64 + d];
+  }
+  for (int t = tid; t < Tw; t += WIN_THREADS) pixof[t] = t / K;
+  for (int i = tid; i < P * P; i += WIN_THREADS) {
+    const int pi = i / P, pj = i % P;
+    relof[i] = ((pi / ws - pj / ws + ws - 1) * (2 * ws - 1) + (pi % ws - pj % ws + ws - 1)) * RS;
   }
   for (int t = tid; t < TT; t += WIN_THREADS) {
     const int wl = t / Tw, tl = t % Tw;
@@ -136,11 +143,10 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
   __syncthreads();
   // QR[t][pp] = (s q_t).Rk[rel(p_t,pp)]     KR[t][pp] = k_t.(s Rq[rel(pp,p_t)])
   for (int i = tid; i < TT * P; i += WIN_THREADS) {
-    const int t = i / P, pp = i % P;
-    const int pt = (t % Tw) / K;
-    const int dy = pt / ws - pp / ws, dx = pt % ws - pp % ws;
-    const float* rk = sRk + ((dy + ws - 1) * (2 * ws - 1) + (dx + ws - 1)) * RS;
-    const float* rq = sRq + ((-dy + ws - 1) * (2 * ws - 1) + (-dx + ws - 1)) * RS;
+    const int t = i / P, pp = i - t * P;
+    const int pt = pixof[t % Tw];
+    const float* rk = sRk + relof[pt * P + pp];
+    const float* rq = sRq + relof[pp * P + pt];
     float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll 8
     for (int d = 0; d < 32; d += 2) {
@@ -194,15 +200,19 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
     // RPE terms, masks, softmax (row-wise over the window's Tw columns)
     float inv[R];
 #pragma unroll
+    int pjc[NCH];                      // pixel of this lane's key columns
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) pjc[c] = pixof[min(c * 32 + lane, Tw - 1)];
+#pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int i = i0 + r, il = i - c0, pi = il / K;
+      const int i = i0 + r, il = i - c0, pi = pixof[il];
       float m = -INFINITY;
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         const int j = c * 32 + lane;
         float s = -INFINITY;
         if (j < Tw) {
-          const int pj = j / K;
+          const int pj = pjc[c];
           s = acc[r][c] + QR[i * P + pj] + KR[(c0 + j) * P + pi];
           const bool masked = (wreg[pi] != wreg[pj]) || (p.self_edge && pi == pj && il != j);
           if (masked) s = -INFINITY;
@@ -252,13 +262,10 @@ __global__ void __launch_bounds__(WIN_THREADS) window_attention_kernel(const Win
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      const int pi = (i0 + r - c0) / K;
-      const int yi = pi / ws, xi = pi % ws;
+      const int* rel = relof + pixof[i0 + r - c0] * P;
       float acc_rv = o[r];
-      for (int pp = 0; pp < P; ++pp) {
-        const int rr = (yi - pp / ws + ws - 1) * (2 * ws - 1) + (xi - pp % ws + ws - 1);
-        acc_rv = fmaf(myab[pp * R + r], sRv[rr * 33 + lane], acc_rv);
-      }
+#pragma unroll 4
+      for (int pp = 0; pp < P; ++pp) acc_rv = fmaf(myab[pp * R + r], sRv[rel[pp] + lane], acc_rv);
       p.out[(size_t)tok_row[i0 + r] * kEmbed + head * 32 + lane] = acc_rv * inv[r];
     }
     __syncwarp();
@@ -315,8 +322,12 @@ stripe_attention_kernel(const float* __restrict__ qkv, int B, int h, int w, int 
   }
 
   float m[ST_RPW], l[ST_RPW], acc[ST_RPW];
+  int pix_i[ST_RPW];                   // pixel (along the stripe) of this warp's query rows
 #pragma unroll
-  for (int r = 0; r < ST_RPW; ++r) { m[r] = -INFINITY; l[r] = 0.f; acc[r] = 0.f; }
+  for (int r = 0; r < ST_RPW; ++r) {
+    m[r] = -INFINITY; l[r] = 0.f; acc[r] = 0.f;
+    pix_i[r] = (q0 + warp * ST_RPW + r) / K;
+  }
 
   for (int t0 = 0; t0 < Lk; t0 += ST_KT) {
     __syncthreads();
@@ -350,6 +361,7 @@ stripe_attention_kernel(const float* __restrict__ qkv, int B, int h, int w, int 
         s[r][1] = fmaf(q4.z, k1[2], s[r][1]); s[r][1] = fmaf(q4.w, k1[3], s[r][1]);
       }
     }
+    const int pix_j0 = (t0 + lane) / K, pix_j1 = (t0 + lane + 32) / K;   // once per tile, not per row
 #pragma unroll
     for (int r = 0; r < ST_RPW; ++r) {
       const int ti = q0 + warp * ST_RPW + r;
@@ -357,7 +369,7 @@ stripe_attention_kernel(const float* __restrict__ qkv, int B, int h, int w, int 
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int tj = t0 + lane + e * 32;
-        const bool masked = (tj >= Lk) || (tj / K == ti / K && tj != ti);   // NMP.py:203-208
+        const bool masked = (tj >= Lk) || ((e ? pix_j1 : pix_j0) == pix_i[r] && tj != ti);   // NMP.py:203-208
         if (masked) s[r][e] = -INFINITY;
         tmax = fmaxf(tmax, s[r][e]);
       }
@@ -454,7 +466,7 @@ int window_attention(const float* qkv, const float* table, int B, int Hp, int Wp
   p.wpc = wpc;
   const size_t TT = (size_t)wpc * Tw;
   const size_t smem = sizeof(float) * ((size_t)3 * NR * 33 + (NR & 1) + (size_t)2 * 32 * (TT + 2) + TT * 32 + 2 * TT * P +
-                                       (size_t)WIN_WARPS * (Tw + P) * R) + sizeof(int) * (TT + (size_t)wpc * P);
+                                       (size_t)WIN_WARPS * (Tw + P) * R) + sizeof(int) * (TT + (size_t)wpc * P + Tw + (size_t)P * P);
   NMRF_REQUIRE(smem <= 227 * 1024, "window_attention: ws=%d K=%d needs %zu B of shared memory", ws, K, smem);
   dim3 grid((p.nwin + wpc - 1) / wpc, kHeads);
 #define NMRF_WIN(RR, NN) if (R == RR && nch <= NN) return launch_window<RR, NN>(p, smem, grid, stream)

@@ -105,7 +105,7 @@ struct TcSmem {
   // dynamic shared memory, 1024-byte aligned: A_hi[2] A_lo[2] B_hi[3] B_lo[3] (16 KB each)
   uint64_t bar[TC_NB];      // one per B buffer: completion of the MMAs of the unit that used it
   uint32_t tmem_base;
-  float mean[TC_BM], rstd[TC_BM];
+  float mean[2][TC_BM], rstd[2][TC_BM];   // double buffered: the next tile's statistics are computed before this tile's epilogue
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -160,10 +160,35 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
 
   if (blockIdx.x < ntiles) load_B(0, 0);        // prologue: the first unit's weights
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const int row0 = tile * TC_BM;
-    const bool has_next_tile = tile + (int)gridDim.x < ntiles;
-    // ---- LayerNorm statistics of the tile's rows (Kx == 128): one warp per 16 rows ----------------
+  // per-tile producer state (set by begin_tile): row pointers of this thread, prefetched raw A values
+  int row0 = 0;
+  bool row_ok = false;
+  const float* xrow = a.X;
+  const float* erow = a.E;
+  // raw (pre-LayerNorm) A values of this thread: 4 chunks of 4 floats per k-block, fetched THREE k-blocks ahead
+  // (the rows come from HBM/L2: ~1-2 us latency vs ~0.4 us of MMA per unit); three buffers used round-robin
+  float4 ar0[4], ar1[4], ar2[4];
+  auto fetch_A = [&](int kb, float4 (&dst)[4]) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int kk = kb * TC_BK + (a_c0 + cc) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row_ok && kk < Ktot) v = (kk < a.Kx) ? *reinterpret_cast<const float4*>(xrow + kk)
+                                               : *reinterpret_cast<const float4*>(erow + (kk - a.Kx));
+      dst[cc] = v;
+    }
+  };
+  // start a tile: row pointers, first three k-blocks of A in flight, LayerNorm statistics into buffer `par`
+  // (Kx == 128: one warp per 16 rows).  The caller provides the barrier before the statistics are read.
+  auto begin_tile = [&](int tile, int par) {
+    row0 = tile * TC_BM;
+    const int g_row = row0 + a_row;
+    row_ok = g_row < a.rows;
+    xrow = a.X + (size_t)(row_ok ? g_row : 0) * a.ldx;
+    erow = a.E ? a.E + (size_t)((row_ok ? g_row : 0) / a.ediv) * a.lde : nullptr;
+    fetch_A(0, ar0);
+    fetch_A(1, ar1);          // k-blocks beyond Ktot read nothing (zero fill)
+    fetch_A(2, ar2);
     if (ln) {
       for (int i = 0; i < TC_BM / 8; ++i) {
         const int lr = warp * (TC_BM / 8) + i, r = row0 + lr;
@@ -172,32 +197,20 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
         const float mean = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
         const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
         const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
-        if (lane == 0) { sm.mean[lr] = mean; sm.rstd[lr] = 1.f / sqrtf(var + 1e-5f); }
+        if (lane == 0) { sm.mean[par][lr] = mean; sm.rstd[par][lr] = 1.f / sqrtf(var + 1e-5f); }
       }
-      __syncthreads();
     }
-    const int g_row = row0 + a_row;
-    const bool row_ok = g_row < a.rows;
-    const float* xrow = a.X + (size_t)(row_ok ? g_row : 0) * a.ldx;
-    const float* erow = a.E ? a.E + (size_t)((row_ok ? g_row : 0) / a.ediv) * a.lde : nullptr;
-    const float mean = ln ? sm.mean[a_row] : 0.f, rstd = ln ? sm.rstd[a_row] : 1.f;
+  };
 
-    // raw (pre-LayerNorm) A values of this thread: 4 chunks of 4 floats per k-block, fetched THREE k-blocks
-    // ahead (the rows come from HBM/L2: ~1-2 us latency vs ~0.4 us of MMA per unit); static register rotation
-    float4 ar0[4], ar1[4], ar2[4];
-    auto fetch_A = [&](int kb, float4* dst) {
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int kk = kb * TC_BK + (a_c0 + cc) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row_ok && kk < Ktot) v = (kk < a.Kx) ? *reinterpret_cast<const float4*>(xrow + kk)
-                                                 : *reinterpret_cast<const float4*>(erow + (kk - a.Kx));
-        dst[cc] = v;
-      }
-    };
-    fetch_A(0, ar0);
-    fetch_A(1, ar1);        // k-blocks beyond Ktot read nothing (zero fill)
-    fetch_A(2, ar2);
+  int par = 0;
+  if (blockIdx.x < ntiles) {
+    begin_tile(blockIdx.x, 0);
+    __syncthreads();
+  }
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const bool has_next_tile = tile + (int)gridDim.x < ntiles;
+    const int cur_row0 = row0;
+    const float mean = ln ? sm.mean[par][a_row] : 0.f, rstd = ln ? sm.rstd[par][a_row] : 1.f;
 
     for (int ut = 0; ut < upt; ++ut, ++unit) {
       const int kb = ut / nnc, nc = ut % nnc;
@@ -208,31 +221,35 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
       // ---- prefetch the next unit's weights (next tile starts again at k-block 0, n-chunk 0) ----------------
       const bool prefetch = (ut + 1 < upt) || has_next_tile;
       if (prefetch) load_B((ut + 1 < upt) ? ut + 1 : 0, (unit + 1) % TC_NB);
-      // ---- A: produced once per k-block (nc == 0): load, LayerNorm, concat, split hi/lo ---------------------
+      // ---- A: produced once per k-block (nc == 0): LayerNorm, concat, split hi/lo from the prefetched registers;
+      //      the buffer is immediately re-armed with k-block kb+3 (three buffers used round-robin: no register moves,
+      //      so the loads stay in flight for three k-blocks of MMAs)
       if (nc == 0) {
-        uint8_t* dh = sA_hi[kb & 1];
-        uint8_t* dl = sA_lo[kb & 1];
+        auto produce = [&](float4 (&buf)[4]) {
+          uint8_t* dh = sA_hi[kb & 1];
+          uint8_t* dl = sA_lo[kb & 1];
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = a_c0 + cc;
-          const int kk = kb * TC_BK + c * 4;
-          float4 v = ar0[cc];
-          if (ln && row_ok && kk < a.Kx) {
-            const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
-            const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
-            v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
-            v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
+          for (int cc = 0; cc < 4; ++cc) {
+            const int c = a_c0 + cc;
+            const int kk = kb * TC_BK + c * 4;
+            float4 v = buf[cc];
+            if (ln && row_ok && kk < a.Kx) {
+              const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
+              const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
+              v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
+              v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
+            }
+            float4 h, l;
+            h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
+            l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
+            const uint32_t so = swz(a_row, c);
+            *reinterpret_cast<float4*>(dh + so) = h;
+            *reinterpret_cast<float4*>(dl + so) = l;
           }
-          float4 h, l;
-          h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
-          l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-          const uint32_t so = swz(a_row, c);
-          *reinterpret_cast<float4*>(dh + so) = h;
-          *reinterpret_cast<float4*>(dl + so) = l;
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) { ar0[cc] = ar1[cc]; ar1[cc] = ar2[cc]; }
-        fetch_A(kb + 3, ar2);                   // in flight for three k-blocks of MMAs
+          fetch_A(kb + 3, buf);
+        };
+        const int which = kb % 3;
+        if (which == 0) produce(ar0); else if (which == 1) produce(ar1); else produce(ar2);
       }
       // B(unit) has landed (only the group just committed for unit+1 may still be in flight)
       if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -258,6 +275,10 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
         umma_commit(&sm.bar[buf]);
       }
     }
+    // ---- next tile: rows, A prefetch and LayerNorm statistics go out BEFORE this tile's epilogue, so their
+    //      latency overlaps the last MMAs and the epilogue --------------------------------------------------
+    if (has_next_tile) begin_tile(tile + (int)gridDim.x, par ^ 1);
+    par ^= 1;
     // ---- wait for the tile's last MMAs, then the epilogue ---------------------------------------------
     {
       const uint32_t last = unit - 1;
@@ -284,18 +305,23 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
         if (n < a.N) {
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.bias) b = *reinterpret_cast<const float4*>(a.bias + n);
+          // all residual loads first (R may alias Y: in-place residual; every element is read before it is written,
+          // by the same thread -- hoisting keeps the 8 loads in flight instead of load->store->load serialisation)
+          float4 rr[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = cur_row0 + q * 32 + it * 4 + srow;
+            rr[it] = (a.R && r < a.rows) ? __ldcg(reinterpret_cast<const float4*>(a.R + (size_t)r * a.ldr + n))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int lr = it * 4 + srow;
-            const int r = row0 + q * 32 + lr;
+            const int r = cur_row0 + q * 32 + lr;
             if (r < a.rows) {
               float4 o = *reinterpret_cast<const float4*>(stage + lr * 36 + scol);
-              o.x = act_fn(o.x + b.x, a.act); o.y = act_fn(o.y + b.y, a.act);
-              o.z = act_fn(o.z + b.z, a.act); o.w = act_fn(o.w + b.w, a.act);
-              if (a.R) {
-                const float4 rr = *reinterpret_cast<const float4*>(a.R + (size_t)r * a.ldr + n);
-                o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-              }
+              o.x = act_fn(o.x + b.x, a.act) + rr[it].x; o.y = act_fn(o.y + b.y, a.act) + rr[it].y;
+              o.z = act_fn(o.z + b.z, a.act) + rr[it].z; o.w = act_fn(o.w + b.w, a.act) + rr[it].w;
               *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
             }
           }

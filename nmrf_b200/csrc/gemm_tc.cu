@@ -15,90 +15,24 @@
 //               produce A if the k-block changed, wait for B(u), fence to the async proxy, __syncthreads, then
 //               ONE thread issues 12 tcgen05.mma (4 k-steps x 3 products) and commits to the unit's mbarrier.
 //               MMA(u) is issued while MMA(u-1) is still running; the weight prefetch runs across tiles.
+//   roles     : warps 0-7 produce (and run the epilogue); warp 8 only issues MMAs.  Producers do not wait for
+//               the issue: they bar.arrive on the unit's named barrier (id 1 + unit%3) and go on filling; the MMA
+//               warp bar.syncs on it.  (tcgen05.mma issue back-pressures on the tensor queue; issuing from a
+//               producer thread stalled that warp's share of the next fill and everybody behind a __syncthreads.)
 //   epilogue  : tcgen05.ld 32x32b (each warp its TMEM lane quarter) -> bias/act/residual -> global.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace nmrf {
 namespace {
+using namespace tc;
 
-constexpr int TC_THREADS = 256;
+constexpr int TC_THREADS = 256;             // producer / epilogue threads (warps 0-7)
+constexpr int TC_BLOCK = TC_THREADS + 32;   // + warp 8: the MMA issuer
 constexpr int TC_BM = 128;
 constexpr int TC_BN = 128;                 // n-chunk per MMA
 constexpr int TC_BK = 32;                  // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;   // 16 KB per operand tile
-constexpr uint32_t SPIN_LIMIT = 1u << 26;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ float rna_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-// bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return;
-  }
-  __trap();
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):
-//   [0,14) start address >> 4, [16,30) LBO >> 4 (=1, unused for swizzled K-major), [32,46) SBO >> 4
-//   (= 1024 B between 8-row groups), [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-// instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format TF32 (=2 at bits 7,10),
-// both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-__device__ __forceinline__ float act_fn(float v, int act) {
-  if (act == 1) return fmaxf(v, 0.f);
-  if (act == 2) return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
-  return v;
-}
-
-// byte offset of the 16-byte chunk (row r, chunk c of 8) inside a [rows x 128 B] SWIZZLE_128B tile
-__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 constexpr int TC_NB = 3;    // B buffers
 struct TcSmem {
@@ -108,16 +42,17 @@ struct TcSmem {
   float mean[2][TC_BM], rstd[2][TC_BM];   // double buffered: the next tile's statistics are computed before this tile's epilogue
 };
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_BLOCK, 1)
 token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int ntiles, int tmem_cols) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   __shared__ TcSmem sm;
   // carve the operand tiles (the dynamic window is 1024-byte aligned by the launch: see launcher)
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA_hi[2] = {base, base + TC_TILE_BYTES};
-  uint8_t* sA_lo[2] = {base + 2 * TC_TILE_BYTES, base + 3 * TC_TILE_BYTES};
-  uint8_t* sB_hi[TC_NB] = {base + 4 * TC_TILE_BYTES, base + 5 * TC_TILE_BYTES, base + 6 * TC_TILE_BYTES};
-  uint8_t* sB_lo[TC_NB] = {base + 7 * TC_TILE_BYTES, base + 8 * TC_TILE_BYTES, base + 9 * TC_TILE_BYTES};
+  // tile order: A_hi[0..1] A_lo[0..1] B_hi[0..2] B_lo[0..2]   (address arithmetic, no pointer arrays -> no local memory)
+  auto sA_hi = [&](int i) { return base + i * TC_TILE_BYTES; };
+  auto sA_lo = [&](int i) { return base + (2 + i) * TC_TILE_BYTES; };
+  auto sB_hi = [&](int i) { return base + (4 + i) * TC_TILE_BYTES; };
+  auto sB_lo = [&](int i) { return base + (7 + i) * TC_TILE_BYTES; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ktot = a.Kx + a.Ke;
@@ -152,13 +87,13 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
       const int r = i >> 3, c = i & 7;
       const size_t goff = (size_t)(n0 + r) * a.ldw + kb * TC_BK + c * 4;
       const uint32_t so = swz(r, c);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_hi[b] + so)), "l"(a.W + goff));
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_lo[b] + so)), "l"(W_lo + goff));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_hi(b) + so)), "l"(a.W + goff));
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_lo(b) + so)), "l"(W_lo + goff));
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
 
-  if (blockIdx.x < ntiles) load_B(0, 0);        // prologue: the first unit's weights
+  if (blockIdx.x < ntiles && warp < 8) load_B(0, 0);        // prologue: the first unit's weights
 
   // per-tile producer state (set by begin_tile): row pointers of this thread, prefetched raw A values
   int row0 = 0;
@@ -204,14 +139,15 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
 
   int par = 0;
   if (blockIdx.x < ntiles) {
-    begin_tile(blockIdx.x, 0);
+    if (warp < 8) begin_tile(blockIdx.x, 0);
     __syncthreads();
   }
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const bool has_next_tile = tile + (int)gridDim.x < ntiles;
     const int cur_row0 = row0;
-    const float mean = ln ? sm.mean[par][a_row] : 0.f, rstd = ln ? sm.rstd[par][a_row] : 1.f;
+    const float mean = (ln && warp < 8) ? sm.mean[par][a_row] : 0.f, rstd = (ln && warp < 8) ? sm.rstd[par][a_row] : 1.f;
 
+    if (warp < 8) {   // ================= producers =================
     for (int ut = 0; ut < upt; ++ut, ++unit) {
       const int kb = ut / nnc, nc = ut % nnc;
       const int buf = unit % TC_NB;
@@ -226,8 +162,8 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
       //      so the loads stay in flight for three k-blocks of MMAs)
       if (nc == 0) {
         auto produce = [&](float4 (&buf)[4]) {
-          uint8_t* dh = sA_hi[kb & 1];
-          uint8_t* dl = sA_lo[kb & 1];
+          uint8_t* dh = sA_hi(kb & 1);
+          uint8_t* dl = sA_lo(kb & 1);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const int c = a_c0 + cc;
@@ -255,15 +191,20 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
       if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
       else asm volatile("cp.async.wait_group 0;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
-      __syncthreads();
-      // ---- MMA issue: one thread, 4 k-steps (8 tf32 = 32 B each) x 3 products -----------------------------------
-      if (tid == 0) {
+      asm volatile("bar.arrive %0, %1;" ::"r"(1 + (int)(unit % TC_NB)), "r"(TC_BLOCK) : "memory");   // hand unit to the MMA warp
+    }
+    } else {          // ================= MMA issuer (warp 8) ========
+    for (int ut = 0; ut < upt; ++ut, ++unit) {
+      const int kb = ut / nnc, nc = ut % nnc;
+      const int buf = unit % TC_NB;
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + buf), "r"(TC_BLOCK) : "memory");      // unit's operands are in shared memory
+      if (lane == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int n0 = nc * TC_BN;
         const int bn = min(TC_BN, a.N - n0);
         const uint32_t idesc = make_idesc(bn);
-        const uint64_t dAh = make_desc(smem_u32(sA_hi[kb & 1])), dAl = make_desc(smem_u32(sA_lo[kb & 1]));
-        const uint64_t dBh = make_desc(smem_u32(sB_hi[buf])), dBl = make_desc(smem_u32(sB_lo[buf]));
+        const uint64_t dAh = make_desc(smem_u32(sA_hi(kb & 1))), dAl = make_desc(smem_u32(sA_lo(kb & 1)));
+        const uint64_t dBh = make_desc(smem_u32(sB_hi(buf))), dBl = make_desc(smem_u32(sB_lo(buf)));
         const uint32_t d = tmem + (uint32_t)n0;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -274,19 +215,21 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
         }
         umma_commit(&sm.bar[buf]);
       }
+      __syncwarp();
+    }
     }
     // ---- next tile: rows, A prefetch and LayerNorm statistics go out BEFORE this tile's epilogue, so their
     //      latency overlaps the last MMAs and the epilogue --------------------------------------------------
-    if (has_next_tile) begin_tile(tile + (int)gridDim.x, par ^ 1);
+    if (warp < 8 && has_next_tile) begin_tile(tile + (int)gridDim.x, par ^ 1);
     par ^= 1;
-    // ---- wait for the tile's last MMAs, then the epilogue ---------------------------------------------
-    {
+    // ---- wait for the tile's last MMAs, then the epilogue (producer warps) ---------------------------
+    if (warp < 8) {
       const uint32_t last = unit - 1;
       mbar_wait(&sm.bar[last % TC_NB], (last / TC_NB) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       __syncwarp();
     }
-    {
+    if (warp < 8) {
       // warp w reads TMEM lanes 32*(w%4)..+32 (its row quarter); warps 0-3 take even 32-column chunks, 4-7 odd.
       // The 32x32 block (lane = row) is transposed through a per-warp staging tile in the (now idle) A buffers so
       // that global traffic is coalesced: 8 lanes cover one row's 128 bytes, a warp instruction covers 4 rows.
@@ -367,7 +310,7 @@ int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t strea
   int cols = 32;
   while (cols < a.N) cols <<= 1;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  token_gemm_tc_kernel<<<grid, TC_THREADS, dyn, stream>>>(a, W_lo, ntiles, cols);
+  token_gemm_tc_kernel<<<grid, TC_BLOCK, dyn, stream>>>(a, W_lo, ntiles, cols);
   count_launch();
   return check_launch("token_gemm_tc");
 }

@@ -39,6 +39,10 @@ const char* nmrf_last_error(void);          /* thread-local, valid until the nex
 /* number of kernels this library has launched since load (bench.py's "gpu_launches") */
 uint64_t nmrf_launch_count(void);
 
+/* attention kernels: 1 = tcgen05 3xTF32 (default), 0 = fp32 FMA.  Process-wide; the environment variable
+ * NMRF_B200_ATTN=simt selects 0 at first use.  (The GEMM path is chosen per call by nmrf_gemm_args.W_lo.) */
+int nmrf_set_attention_impl(int tensor_cores);
+
 /* ---- generic fused token GEMM -------------------------------------------------------------
  * Y[r, n] = act( sum_k A[r,k] * W[n,k] + bias[n] ) (+ R[r,n])
  * A[r, :] = concat( LN?(X[r, 0:Kx]), E[r / ediv, 0:Ke] ),   W is [N, ldw] with ldw >= Kx+Ke.

@@ -1,6 +1,7 @@
 // extern "C" surface of libnmrf_b200.so (see include/nmrf_b200.h).  Argument validation,
 // error text, launch counting; the kernels live in the sibling translation units.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include "common.cuh"
 
@@ -33,6 +34,7 @@ int prop_head_tail(const float*, const float*, const float*, const int64_t*, int
 int proposal_attention(const float*, int, int, float*, cudaStream_t);
 int window_attention(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int stripe_attention(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+int stripe_attention_tc(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int,
                     int, int, float, float*, float*, cudaStream_t);
 int zero_pad_rows(float*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -45,6 +47,18 @@ int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const f
 
 using namespace nmrf;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+// NMRF_B200_ATTN=simt selects the fp32-FMA attention kernels (default: tcgen05 3xTF32)
+static std::atomic<int> g_attn_tc{-1};
+static bool attn_on_tensor_cores() {
+  int v = g_attn_tc.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("NMRF_B200_ATTN");
+    v = !(e && (e[0] == 's' || e[0] == 'S'));
+    g_attn_tc.store(v, std::memory_order_relaxed);
+  }
+  return v != 0;
+}
 
 extern "C" {
 
@@ -72,6 +86,10 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
   }
   return token_gemm_simt(*a, ST(stream));
 }
+int nmrf_set_attention_impl(int tensor_cores) {
+  g_attn_tc.store(tensor_cores ? 1 : 0, std::memory_order_relaxed);
+  return NMRF_OK;
+}
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
   return split_tf32(w, hi, lo, (long long)n, ST(stream));
 }
@@ -86,6 +104,12 @@ int nmrf_prop_gather(const float* cv, const int64_t* seeds, int P, int G, int D,
 }
 int nmrf_stripe_attention(const float* qkv, int B, int h, int w, int K, const float* gv0, const float* gv1, float* out,
                           void* stream) {
+  if (attn_on_tensor_cores()) {
+    NMRF_REQUIRE(qkv && gv0 && gv1 && out, "stripe_attention: null pointer");
+    NMRF_REQUIRE(B * (h > w ? h : w) <= 65535, "stripe_attention: too many stripes for grid.y");
+    NMRF_REQUIRE(K >= 1, "stripe_attention: K=%d", K);
+    return stripe_attention_tc(qkv, B, h, w, K, gv0, gv1, out, ST(stream));
+  }
   return stripe_attention(qkv, B, h, w, K, gv0, gv1, out, ST(stream));
 }
 int nmrf_prop_head_tail(const float* hidden, const float* w, const float* b, const int64_t* seeds, int T, float* labels,

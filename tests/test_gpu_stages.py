@@ -181,8 +181,16 @@ def test_prop_head_tail(ops):
     assert rel_err(out, ref) <= 2e-6
 
 
-@pytest.mark.parametrize("B,h,w,K", [(1, 7, 13, 4), (2, 5, 9, 2), (1, 40, 3, 3), (1, 20, 70, 4), (1, 1, 1, 4)])
-def test_stripe_attention(ops, stress, B, h, w, K):
+@pytest.fixture(params=[1, 0], ids=["tcgen05", "fma"])
+def attn_impl(request):
+    from nmrf_b200 import _lib
+    _lib.lib.nmrf_set_attention_impl(request.param)
+    yield request.param
+    _lib.lib.nmrf_set_attention_impl(1)
+
+
+@pytest.mark.parametrize("B,h,w,K", [(1, 7, 13, 4), (2, 5, 9, 2), (1, 40, 3, 3), (1, 20, 70, 4), (1, 1, 1, 4), (1, 68, 120, 4)])
+def test_stripe_attention(ops, stress, attn_impl, B, h, w, K):
     g = torch.Generator().manual_seed(h * w)
     qkv = torch.randn(B, h, w, K, 384, generator=g)
     qkv[..., :256] *= 2.0                                                   # peaky softmax

@@ -17,7 +17,13 @@ namespace nmrf {
 namespace {
 using namespace tc;
 
-constexpr float kScale = 0.17677669529663687f;   // 32^-0.5
+// softmax in base 2: Q is scaled by 32^-0.5 * log2(e) once, so p = 2^(S - m) (one MUFU.EX2, <= 2 ulp) == e^(s - m)
+constexpr float kScaleLog2e = 0.17677669529663687f * 1.4426950408889634f;
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr int AT_THREADS = 128;
 constexpr int AT_KC = 32;                         // keys per chunk
 constexpr int AT_QTILE = 128 * 128;               // bytes of a [128 x 32 fp32] tile
@@ -96,7 +102,7 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     for (int c = 0; c < 8; ++c) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (valid) v = *reinterpret_cast<const float4*>(src + c * 4);
-      v.x *= kScale; v.y *= kScale; v.z *= kScale; v.w *= kScale;
+      v.x *= kScaleLog2e; v.y *= kScaleLog2e; v.z *= kScaleLog2e; v.w *= kScaleLog2e;
       float4 hi, lo;
       split4(v, hi, lo);
       const uint32_t so = swz(tid, c);
@@ -139,26 +145,36 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
   const uint64_t dVh = make_desc(smem_u32(sVh)), dVl = make_desc(smem_u32(sVl));
   const uint64_t dPh = make_desc(smem_u32(sPh)), dPl = make_desc(smem_u32(sPl));
 
+  // shared-memory offsets of this thread's staging items (independent of the chunk)
+  uint32_t k_off[2], v_off[2][4], p_off[8];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int i = tid + 128 * e, key = i >> 3, c8 = i & 7;
+    k_off[e] = swz(key, c8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = c8 * 4 + j;
+      v_off[e][j] = (uint32_t)(d * 128 + (((key >> 2) ^ (d & 7)) << 4) + (key & 3) * 4);
+    }
+  }
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8) p_off[c8] = swz(tid, c8);
+
   fetch_kv(0);
   for (int c = 0; c < nchunks; ++c) {
     // ---- stage K_c (rows = keys) and V_c^T (rows = dims, columns = keys); previous chunk's MMAs are complete ----
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const int i = tid + 128 * e;
-      const int key = i >> 3, c8 = i & 7;
       float4 hi, lo;
       split4(kr[e], hi, lo);
-      const uint32_t so = swz(key, c8);
-      *reinterpret_cast<float4*>(sKh + so) = hi;
-      *reinterpret_cast<float4*>(sKl + so) = lo;
+      *reinterpret_cast<float4*>(sKh + k_off[e]) = hi;
+      *reinterpret_cast<float4*>(sKl + k_off[e]) = lo;
       split4(vr[e], hi, lo);
       const float hv[4] = {hi.x, hi.y, hi.z, hi.w}, lv[4] = {lo.x, lo.y, lo.z, lo.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int d = c8 * 4 + j;
-        const uint32_t vo = (uint32_t)(d * 128 + (((key >> 2) ^ (d & 7)) << 4) + (key & 3) * 4);
-        *reinterpret_cast<float*>(sVh + vo) = hv[j];
-        *reinterpret_cast<float*>(sVl + vo) = lv[j];
+        *reinterpret_cast<float*>(sVh + v_off[e][j]) = hv[j];
+        *reinterpret_cast<float*>(sVl + v_off[e][j]) = lv[j];
       }
     }
     if (c + 1 < nchunks) fetch_kv(c + 1);                       // in flight during this chunk's MMAs and softmax
@@ -182,20 +198,26 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     float s[32];
     tmem_ld32(tmem + t_lane, s);
     // ---- mask + online softmax on this thread's row ---------------------------------------------------------------
-    float cmax = -INFINITY;
+    // only chunks that reach past the stripe's end or touch this row's own pixel need the mask (NMP.py:203-208)
+    const int t_lo = c * AT_KC;
+    if (t_lo + AT_KC > Lk || (t_lo < pix_hi && t_lo + AT_KC > pix_lo)) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int tj = c * AT_KC + j;
-      const bool masked = (tj >= Lk) || (tj >= pix_lo && tj < pix_hi && tj != ti);     // NMP.py:203-208
-      s[j] = masked ? -INFINITY : s[j];
-      cmax = fmaxf(cmax, s[j]);
+      for (int j = 0; j < 32; ++j) {
+        const int tj = t_lo + j;
+        const bool masked = (tj >= Lk) || (tj >= pix_lo && tj < pix_hi && tj != ti);
+        s[j] = masked ? -INFINITY : s[j];
+      }
     }
+    float cmax = s[0];
+#pragma unroll
+    for (int j = 1; j < 32; ++j) cmax = fmaxf(cmax, s[j]);
     const float mnew = fmaxf(m, cmax);
-    const float scale = (mnew == -INFINITY) ? 1.f : expf(m - mnew);
+    const float msafe = (mnew == -INFINITY) ? 0.f : mnew;        // a fully masked prefix keeps p = 0, scale = 1
+    const float scale = ex2(m - msafe);
     float psum = 0.f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-      s[j] = (mnew == -INFINITY) ? 0.f : expf(s[j] - mnew);
+      s[j] = ex2(s[j] - msafe);
       psum += s[j];
     }
     l = l * scale + psum;
@@ -204,9 +226,8 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     for (int c8 = 0; c8 < 8; ++c8) {
       float4 hi, lo;
       split4(make_float4(s[c8 * 4], s[c8 * 4 + 1], s[c8 * 4 + 2], s[c8 * 4 + 3]), hi, lo);
-      const uint32_t so = swz(tid, c8);
-      *reinterpret_cast<float4*>(sPh + so) = hi;
-      *reinterpret_cast<float4*>(sPl + so) = lo;
+      *reinterpret_cast<float4*>(sPh + p_off[c8]) = hi;
+      *reinterpret_cast<float4*>(sPl + p_off[c8]) = lo;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -223,14 +244,12 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
       umma_commit(&sm.bar_o);
     }
     __syncwarp();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] *= scale;                 // overlaps the PV MMAs
     mbar_wait(&sm.bar_o, c & 1);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     float pv[32];
     tmem_ld32(tmem + t_lane + 32, pv);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) o[j] += pv[j];
+    for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], scale, pv[j]);
   }
 
   // ---- epilogue: normalise + LePE (NMP.py:433-449), see attention.cu for the derivation ------------------------

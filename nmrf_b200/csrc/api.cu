@@ -26,6 +26,7 @@ int check_launch(const char* what) {
 
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
 int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
+int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
                      float*, float*, int64_t*, cudaStream_t);
@@ -82,7 +83,8 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
     const int kpad = ((a->Kx + a->Ke + 31) / 32) * 32;
     NMRF_REQUIRE(a->N % 16 == 0 && a->N <= 512, "token_gemm(tc): N=%d must be a multiple of 16, <= 512", a->N);
     NMRF_REQUIRE(a->ldw % 32 == 0 && a->ldw >= kpad, "token_gemm(tc): ldw=%d must be a multiple of 32 and >= %d", a->ldw, kpad);
-    return token_gemm_tc(*a, a->W_lo, ST(stream));
+    static const bool v4 = [] { const char* e = getenv("NMRF_B200_GEMM_V"); return e && e[0] == '4'; }();
+    return v4 ? token_gemm_tc(*a, a->W_lo, ST(stream)) : token_gemm_tc5(*a, a->W_lo, ST(stream));
   }
   return token_gemm_simt(*a, ST(stream));
 }

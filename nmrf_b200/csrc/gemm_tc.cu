@@ -74,6 +74,7 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
   const uint32_t tmem = sm.tmem_base;
 
   uint32_t unit = 0;                 // global unit counter of this CTA (B buffer = unit % 3, use = unit / 3)
+  uint32_t akb = 0, abuf = 0;        // global k-block counter: A buffer = akb & 1 alternates across tiles as well
   const int upt = nkb * nnc;         // units per tile
 
   // producer mapping for A: thread -> (row = tid/2, 16 consecutive k = 4 chunks of 16 B)
@@ -162,8 +163,8 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
       //      so the loads stay in flight for three k-blocks of MMAs)
       if (nc == 0) {
         auto produce = [&](float4 (&buf)[4]) {
-          uint8_t* dh = sA_hi(kb & 1);
-          uint8_t* dl = sA_lo(kb & 1);
+          uint8_t* dh = sA_hi(akb & 1);
+          uint8_t* dl = sA_lo(akb & 1);
 #pragma unroll
           for (int cc = 0; cc < 4; ++cc) {
             const int c = a_c0 + cc;
@@ -186,6 +187,7 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
         };
         const int which = kb % 3;
         if (which == 0) produce(ar0); else if (which == 1) produce(ar1); else produce(ar2);
+        ++akb;
       }
       // B(unit) has landed (only the group just committed for unit+1 may still be in flight)
       if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -197,13 +199,14 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
     for (int ut = 0; ut < upt; ++ut, ++unit) {
       const int kb = ut / nnc, nc = ut % nnc;
       const int buf = unit % TC_NB;
+      if (nc == 0) abuf = (akb++) & 1;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + buf), "r"(TC_BLOCK) : "memory");      // unit's operands are in shared memory
       if (lane == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int n0 = nc * TC_BN;
         const int bn = min(TC_BN, a.N - n0);
         const uint32_t idesc = make_idesc(bn);
-        const uint64_t dAh = make_desc(smem_u32(sA_hi(kb & 1))), dAl = make_desc(smem_u32(sA_lo(kb & 1)));
+        const uint64_t dAh = make_desc(smem_u32(sA_hi(abuf))), dAl = make_desc(smem_u32(sA_lo(abuf)));
         const uint64_t dBh = make_desc(smem_u32(sB_hi(buf))), dBl = make_desc(smem_u32(sB_lo(buf)));
         const uint32_t d = tmem + (uint32_t)n0;
 #pragma unroll

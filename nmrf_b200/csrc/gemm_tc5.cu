@@ -1,13 +1,14 @@
 // Fused token GEMM on tcgen05, warp-specialised (v5).  Same arithmetic as gemm_tc.cu (error-compensated 3xTF32,
 // LayerNorm / concat prologue, bias / ReLU / GELU / residual epilogue); different schedule:
 //
-//   warps 0-3   producers   thread r = token row r of the tile: LayerNorm statistics of its own row, raw A values
-//                           prefetched two k-blocks ahead in registers, hi/lo split into the swizzled A tiles
-//                           (st.shared), weight tiles by cp.async one unit ahead; hand-off to the MMA warp through a
-//                           per-slot named barrier (bar.arrive), never waits for the issue
-//   warp  4     MMA issuer  bar.sync on the slot, 12 tcgen05.mma (4 k-steps x {lo.hi, hi.lo, hi.hi}) per unit,
+//   warps 0-7   producers   two threads per token row: LayerNorm statistics (cooperative, coalesced, computed for the NEXT
+//                           tile while this tile's last units are produced), raw A values prefetched three k-blocks
+//                           ahead in registers, hi/lo split into the swizzled A tiles (st.shared), weight tiles by
+//                           cp.async one unit ahead; hand-off to the MMA warp through a per-slot named barrier
+//                           (bar.arrive), never waits for the issue
+//   warp  8     MMA issuer  bar.sync on the slot, 12 tcgen05.mma (4 k-steps x {lo.hi, hi.lo, hi.hi}) per unit,
 //                           tcgen05.commit -> slot mbarrier; after the tile's last unit commit -> acc_full[stage]
-//   warps 5-12  epilogue    wait acc_full[stage]; tcgen05.ld 32x32b per warp (its TMEM lane quarter), transpose through a
+//   warps 9-16  epilogue    wait acc_full[stage]; tcgen05.ld 32x32b per warp (its TMEM lane quarter), transpose through a
 //                           private smem tile so global traffic is coalesced (8 lanes = one row's 128 B), bias, activation,
 //                           residual, store; mbarrier.arrive acc_empty[stage]
 //
@@ -24,10 +25,11 @@ using namespace tc;
 
 constexpr int G5_BM = 128, G5_BN = 128, G5_BK = 32, G5_NPASS = 256, G5_NB = 3;
 constexpr int G5_TILE = G5_BM * G5_BK * 4;          // 16 KB operand tile
-constexpr int G5_PROD = 128;                        // producer threads (warps 0-3)
-constexpr int G5_MMA_WARP = 4;
-constexpr int G5_EPI_WARP0 = 5, G5_EPI_WARPS = 8;
-constexpr int G5_BLOCK = (G5_EPI_WARP0 + G5_EPI_WARPS) * 32;   // 416
+constexpr int G5_PROD = 256;                        // producer threads (warps 0-7)
+constexpr int G5_MMA_WARP = 8;
+constexpr int G5_EPI_WARP0 = 9, G5_EPI_WARPS = 8;
+constexpr int G5_BLOCK = (G5_EPI_WARP0 + G5_EPI_WARPS) * 32;   // 544
+constexpr int G5_STATS_BAR = 4;                     // named barrier of the producers (LayerNorm statistics hand-over)
 constexpr int G5_HANDOFF = G5_PROD + 32;            // named-barrier population: producers arrive, MMA warp syncs
 constexpr int G5_STAGE_FLOATS = 32 * 36;            // per-epilogue-warp transpose tile
 constexpr int G5_DYN = 10 * G5_TILE + G5_EPI_WARPS * G5_STAGE_FLOATS * 4 + 1024;
@@ -37,6 +39,7 @@ struct G5Smem {
   uint64_t acc_full[2];       // accumulator stage holds a finished tile (tcgen05.commit)
   uint64_t acc_empty[2];      // epilogue has drained the stage (256 arrivals)
   uint32_t tmem_base;
+  float mean[2][G5_BM], rstd[2][G5_BM];   // LayerNorm statistics, double buffered across tiles
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -84,8 +87,9 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // =============================================== producers ===============================================
+    const int a_row = tid >> 1, a_c0 = (tid & 1) * 4;       // thread -> (row, 16 consecutive k = 4 chunks of 16 B)
     auto load_B = [&](const TileCoord& tc_, int ut, int slot) {
       const int kb = ut / tc_.nnc, n0 = tc_.n_base + (ut % tc_.nnc) * G5_BN;
       const int bn = min(G5_BN, a.N - n0);
@@ -98,68 +102,70 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // LayerNorm statistics of a tile's 128 rows into buffer `par` (Kx == 128): one warp per 16 rows, coalesced
+    auto tile_stats = [&](int row0, int par) {
+      for (int i = 0; i < G5_BM / 8; ++i) {
+        const int lr = warp * (G5_BM / 8) + i, r = row0 + lr;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < a.rows) v = *reinterpret_cast<const float4*>(a.X + (size_t)r * a.ldx + lane * 4);
+        const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
+        const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+        const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
+        if (lane == 0) { sm.mean[par][lr] = mu; sm.rstd[par][lr] = 1.f / sqrtf(var + 1e-5f); }
+      }
+    };
     uint32_t unit = 0;
     uint32_t akb = 0;          // k-blocks produced so far by this CTA: A buffer = akb & 1 (alternates ACROSS tiles too, so the
                                // buffer being rewritten was last read two k-blocks -- at least two units -- ago)
-    int prev_row0 = -1;
-    float mean = 0.f, rstd = 1.f;
-    if ((int)blockIdx.x < ntiles) load_B(coord(blockIdx.x), 0, 0);
+    int par = 0;
+    if ((int)blockIdx.x < ntiles) {
+      load_B(coord(blockIdx.x), 0, 0);
+      if (ln) tile_stats(coord(blockIdx.x).row0, 0);
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(G5_STATS_BAR), "r"(G5_PROD) : "memory");
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
       const TileCoord tc_ = coord(t);
       const bool has_next = t + (int)gridDim.x < ntiles;
-      const int g_row = tc_.row0 + tid;
+      const int g_row = tc_.row0 + a_row;
       const bool row_ok = g_row < a.rows;
       const float* xrow = a.X + (size_t)(row_ok ? g_row : 0) * a.ldx;
       const float* erow = a.E ? a.E + (size_t)((row_ok ? g_row : 0) / a.ediv) * a.lde : nullptr;
-      float4 ar0[8], ar1[8];                 // raw A values of two k-blocks in flight
-      auto fetch_A = [&](int kb, float4 (&dst)[8]) {
+      const float mean = ln ? sm.mean[par][a_row] : 0.f, rstd = ln ? sm.rstd[par][a_row] : 1.f;
+      float4 ar0[4], ar1[4], ar2[4];          // raw A values of three k-blocks in flight (round-robin, no register moves)
+      auto fetch_A = [&](int kb, float4 (&dst)[4]) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int kk = kb * G5_BK + c * 4;
+        for (int cc = 0; cc < 4; ++cc) {
+          const int kk = kb * G5_BK + (a_c0 + cc) * 4;
           const float* p = (kk < a.Kx) ? xrow + kk : erow + (kk - a.Kx);
-          dst[c] = (row_ok && kk < Ktot) ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+          dst[cc] = (row_ok && kk < Ktot) ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       };
-      if (ln && tc_.row0 != prev_row0) {      // LayerNorm statistics of this thread's own row (two passes, Kx == 128)
-        float s = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-          const float4 v = row_ok ? *reinterpret_cast<const float4*>(xrow + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-          s += (v.x + v.y) + (v.z + v.w);
-        }
-        mean = s * (1.f / 128.f);
-        float q = 0.f;
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-          const float4 v = row_ok ? *reinterpret_cast<const float4*>(xrow + c * 4) : make_float4(mean, mean, mean, mean);
-          const float dx = v.x - mean, dy = v.y - mean, dz = v.z - mean, dw = v.w - mean;
-          q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-        }
-        rstd = 1.f / sqrtf(q * (1.f / 128.f) + 1e-5f);
-        prev_row0 = tc_.row0;
-      }
       fetch_A(0, ar0);
       fetch_A(1, ar1);
+      fetch_A(2, ar2);
       const int upt = nkb * tc_.nnc;
+      const int stats_at = upt > 3 ? upt - 3 : 0;            // next tile's statistics go out while the last units are produced
       for (int ut = 0; ut < upt; ++ut, ++unit) {
         const int kb = ut / tc_.nnc, nc = ut - kb * tc_.nnc;
         const int slot = unit % G5_NB;
         // MMAs of unit-2 (and, cumulatively, all earlier ones) are complete: frees B slot (unit+1)%3 and the A buffer of
-        // k-block kb-2.  unit-2 is the newest unit whose barrier phase is unambiguous (its slot is next used by unit+1).
+        // k-block akb-2.  unit-2 is the newest unit whose barrier phase is unambiguous (its slot is next used by unit+1).
         if (unit >= 2) mbar_wait(&sm.done[(unit - 2) % G5_NB], ((unit - 2) / G5_NB) & 1);
         const bool prefetch = (ut + 1 < upt) || has_next;
         if (prefetch) {
           if (ut + 1 < upt) load_B(tc_, ut + 1, (unit + 1) % G5_NB);
           else load_B(coord(t + gridDim.x), 0, (unit + 1) % G5_NB);
         }
+        if (ut == stats_at && has_next && ln) tile_stats(coord(t + gridDim.x).row0, par ^ 1);
         if (nc == 0) {
-          auto produce = [&](float4 (&buf)[8]) {
+          auto produce = [&](float4 (&buf)[4]) {
             uint8_t* dh = sA_hi(akb & 1);
             uint8_t* dl = sA_lo(akb & 1);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
+            for (int cc = 0; cc < 4; ++cc) {
+              const int c = a_c0 + cc;
               const int kk = kb * G5_BK + c * 4;
-              float4 v = buf[c];
+              float4 v = buf[cc];
               if (ln && row_ok && kk < a.Kx) {
                 const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
                 const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
@@ -169,13 +175,14 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
               float4 h, l;
               h.x = rna_tf32(v.x); h.y = rna_tf32(v.y); h.z = rna_tf32(v.z); h.w = rna_tf32(v.w);
               l.x = rna_tf32(v.x - h.x); l.y = rna_tf32(v.y - h.y); l.z = rna_tf32(v.z - h.z); l.w = rna_tf32(v.w - h.w);
-              const uint32_t so = swz(tid, c);
+              const uint32_t so = swz(a_row, c);
               *reinterpret_cast<float4*>(dh + so) = h;
               *reinterpret_cast<float4*>(dl + so) = l;
             }
-            fetch_A(kb + 2, buf);
+            fetch_A(kb + 3, buf);
           };
-          if (kb & 1) produce(ar1); else produce(ar0);
+          const int which = kb % 3;
+          if (which == 0) produce(ar0); else if (which == 1) produce(ar1); else produce(ar2);
           ++akb;
         }
         if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -183,6 +190,9 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "r"(G5_HANDOFF) : "memory");
       }
+      // the next tile's statistics (written by other warps) become visible to every producer
+      asm volatile("bar.sync %0, %1;" ::"r"(G5_STATS_BAR), "r"(G5_PROD) : "memory");
+      par ^= 1;
     }
   } else if (warp == G5_MMA_WARP) {
     // =============================================== MMA issuer ===============================================

@@ -67,6 +67,8 @@ typedef struct {
   const float* W_lo;
 } nmrf_gemm_args;
 int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
+/* debug tooling: device buffer of 4096 int64 that CTA 0 of the tensor-core GEMM fills with clock64() stamps (NULL = off) */
+int nmrf_debug_set_trace(void* dev_i64_4096);
 /* hi = rna_tf32(w), lo = rna_tf32(w - hi), elementwise over n floats (device pointers) */
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
 

@@ -40,6 +40,7 @@ SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
     "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
     "nmrf_set_attention_impl": [_I],
+    "nmrf_debug_set_trace": [_P],
     "nmrf_cost_volume_topk": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, POINTER(SeedWeights), _P, _P, _P, _P],
     "nmrf_prop_gather": [_P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P],
     "nmrf_stripe_attention": [_P, _I, _I, _I, _I, _P, _P, _P, _P],

@@ -27,6 +27,7 @@ int check_launch(const char* what) {
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
 int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
+int gemm_set_trace(long long* dev_ptr);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
                      float*, float*, int64_t*, cudaStream_t);
@@ -92,6 +93,7 @@ int nmrf_set_attention_impl(int tensor_cores) {
   g_attn_tc.store(tensor_cores ? 1 : 0, std::memory_order_relaxed);
   return NMRF_OK;
 }
+int nmrf_debug_set_trace(void* dev_i64_4096) { return gemm_set_trace(reinterpret_cast<long long*>(dev_i64_4096)); }
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
   return split_tf32(w, hi, lo, (long long)n, ST(stream));
 }

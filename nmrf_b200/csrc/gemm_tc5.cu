@@ -48,6 +48,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 struct TileCoord { int row0, n_base, npass, nnc; };
 
+// optional cycle trace of CTA 0 (debug tooling: nmrf_debug_set_trace); slot layout documented in tools/gemm_trace.py
+__device__ long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(long long* tp, int idx) {
+  if (tp && idx < 4096) tp[idx] = clock64();
+}
+
 __global__ void __launch_bounds__(G5_BLOCK, 1)
 token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int n_rb, int n_np) {
   extern __shared__ __align__(1024) uint8_t dsm[];
@@ -60,14 +66,15 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
   float* stage_base = reinterpret_cast<float*>(base + 10 * G5_TILE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long* const tp = (blockIdx.x == 0 && (tid == 0 || tid == G5_MMA_WARP * 32 || tid == G5_EPI_WARP0 * 32)) ? g_trace : nullptr;
   const int Ktot = a.Kx + a.Ke;
   const int nkb = (Ktot + G5_BK - 1) / G5_BK;
   const int ntiles = n_rb * n_np;
   const bool ln = a.ln_gamma != nullptr;
   auto coord = [&](int t) {
     TileCoord c;
-    c.row0 = (t / n_np) * G5_BM;
-    c.n_base = (t % n_np) * G5_NPASS;
+    c.row0 = (t % n_rb) * G5_BM;           // pass-major order: with a persistent stride of gridDim.x every CTA gets the same
+    c.n_base = (t / n_rb) * G5_NPASS;      // mix of wide (256-column) and narrow passes
     c.npass = min(G5_NPASS, a.N - c.n_base);
     c.nnc = (c.npass + G5_BN - 1) / G5_BN;
     return c;
@@ -150,12 +157,15 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
         const int slot = unit % G5_NB;
         // MMAs of unit-2 (and, cumulatively, all earlier ones) are complete: frees B slot (unit+1)%3 and the A buffer of
         // k-block akb-2.  unit-2 is the newest unit whose barrier phase is unambiguous (its slot is next used by unit+1).
+        trace(tp, unit * 8 + 0);
         if (unit >= 2) mbar_wait(&sm.done[(unit - 2) % G5_NB], ((unit - 2) / G5_NB) & 1);
+        trace(tp, unit * 8 + 1);
         const bool prefetch = (ut + 1 < upt) || has_next;
         if (prefetch) {
           if (ut + 1 < upt) load_B(tc_, ut + 1, (unit + 1) % G5_NB);
           else load_B(coord(t + gridDim.x), 0, (unit + 1) % G5_NB);
         }
+        trace(tp, unit * 8 + 2);
         if (ut == stats_at && has_next && ln) tile_stats(coord(t + gridDim.x).row0, par ^ 1);
         if (nc == 0) {
           auto produce = [&](float4 (&buf)[4]) {
@@ -185,10 +195,13 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
           if (which == 0) produce(ar0); else if (which == 1) produce(ar1); else produce(ar2);
           ++akb;
         }
+        trace(tp, unit * 8 + 3);
         if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
         else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        trace(tp, unit * 8 + 4);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "r"(G5_HANDOFF) : "memory");
+        trace(tp, unit * 8 + 5);
       }
       // the next tile's statistics (written by other warps) become visible to every producer
       asm volatile("bar.sync %0, %1;" ::"r"(G5_STATS_BAR), "r"(G5_PROD) : "memory");
@@ -209,7 +222,9 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
         const int kb = ut / tc_.nnc, nc = ut - kb * tc_.nnc;
         const int slot = unit % G5_NB;
         if (nc == 0) abuf = (akb++) & 1;
+        trace(tp, 2048 + unit * 4 + 0);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G5_HANDOFF) : "memory");
+        trace(tp, 2048 + unit * 4 + 1);
         if (lane == 0) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int bn = min(G5_BN, tc_.npass - nc * G5_BN);
@@ -228,6 +243,7 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
           if (ut == upt - 1) umma_commit(&sm.acc_full[as]);
         }
         __syncwarp();
+        trace(tp, 2048 + unit * 4 + 2);
       }
     }
   } else {
@@ -241,7 +257,9 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
       const TileCoord tc_ = coord(t);
       const int as = it & 1;
+      trace(tp, 3584 + it * 4 + 0);
       mbar_wait(&sm.acc_full[as], (it >> 1) & 1);
+      trace(tp, 3584 + it * 4 + 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int nchunks = (tc_.npass + 31) / 32;
       for (int ch = half; ch < nchunks; ch += 2) {
@@ -278,6 +296,7 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(&sm.acc_empty[as]);
+      trace(tp, 3584 + it * 4 + 2);
     }
   }
 
@@ -289,6 +308,10 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
 }
 
 }  // namespace
+
+int gemm_set_trace(long long* dev_ptr) {
+  return cudaMemcpyToSymbol(g_trace, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? NMRF_OK : NMRF_ERR_CUDA;
+}
 
 int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream) {
   static int num_sms = 0;

@@ -1,0 +1,45 @@
+"""Cycle-level trace of CTA 0 of the warp-specialised tcgen05 GEMM (run under gpurun).
+Stamps (clock64): producer thread 0: unit*8 + {0 loop top, 1 after done-wait, 2 after B prefetch issue, 3 after A produce,
+4 after cp.async wait, 5 after hand-off}; MMA lane 0: 2048 + unit*4 + {0 before bar.sync, 1 after, 2 after issue+commit};
+epilogue warp 0 lane 0: 3584 + tile*4 + {0 before acc_full wait, 1 after, 2 after drain}."""
+import os, sys, json
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from nmrf_b200 import _lib, ops
+
+dev = "cuda"
+g = torch.Generator().manual_seed(0)
+out = {}
+for name, rows, Kx, Ke, N, ln, act, res in [("fc2", 34560, 512, 0, 128, False, 0, True), ("qkv", 34560, 128, 32, 384, True, 0, False),
+                                              ("fc1", 34560, 128, 0, 512, True, 2, False), ("proj", 34560, 128, 0, 128, False, 0, True)]:
+    X = torch.randn(rows, Kx, generator=g).to(dev)
+    E = torch.randn(rows, Ke, generator=g).to(dev) if Ke else None
+    W = (torch.randn(N, Kx + Ke, generator=g) / (Kx + Ke) ** 0.5).to(dev)
+    hi, lo = ops.split_tf32(W)
+    b = torch.randn(N, generator=g).to(dev)
+    gam, bet = torch.ones(Kx, device=dev), torch.zeros(Kx, device=dev)
+    R = torch.randn(rows, N, generator=g).to(dev) if res else None
+    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, W_lo=lo)
+    for _ in range(3):
+        ops.token_gemm(X, hi, **kw)
+    tr = torch.zeros(4096, dtype=torch.int64, device=dev)
+    _lib.check(_lib.lib.nmrf_debug_set_trace(tr.data_ptr()), "set_trace")
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record(); ops.token_gemm(X, hi, **kw); e.record(); torch.cuda.synchronize()
+    _lib.check(_lib.lib.nmrf_debug_set_trace(None), "set_trace")
+    t = tr.cpu().tolist()
+    t0 = min(v for v in t if v > 0)
+    prod = [[(t[u * 8 + k] - t0) if t[u * 8 + k] else None for k in range(6)] for u in range(40) if t[u * 8]]
+    mma = [[(t[2048 + u * 4 + k] - t0) if t[2048 + u * 4 + k] else None for k in range(3)] for u in range(40) if t[2048 + u * 4]]
+    epi = [[(t[3584 + i * 4 + k] - t0) if t[3584 + i * 4 + k] else None for k in range(3)] for i in range(8) if t[3584 + i * 4]]
+    out[name] = dict(us=s.elapsed_time(e) * 1e3, producer=prod, mma=mma, epilogue=epi)
+    print(name, f"{s.elapsed_time(e)*1e3:.1f} us")
+    print("  producer (top, +wait, +Bissue, +Aprod, +cpwait, +handoff):")
+    for u, r in enumerate(prod[:24]):
+        print("   u%02d" % u, r[0], [r[k] - r[k - 1] for k in range(1, 6)])
+    print("  mma (before sync, wait, issue):")
+    for u, r in enumerate(mma[:24]):
+        print("   u%02d" % u, r[0], r[1] - r[0], r[2] - r[1])
+    print("  epilogue (start, wait, drain):", [(r[0], r[1] - r[0], r[2] - r[1]) for r in epi])
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", "gemm_trace.json"), "w"))

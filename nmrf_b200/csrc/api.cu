@@ -28,6 +28,8 @@ int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
 int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int gemm_set_trace(long long* dev_ptr);
+int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
+int gemm6_set_trace(long long* dev_ptr);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
                      float*, float*, int64_t*, cudaStream_t);
@@ -84,8 +86,11 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
     const int kpad = ((a->Kx + a->Ke + 31) / 32) * 32;
     NMRF_REQUIRE(a->N % 16 == 0 && a->N <= 512, "token_gemm(tc): N=%d must be a multiple of 16, <= 512", a->N);
     NMRF_REQUIRE(a->ldw % 32 == 0 && a->ldw >= kpad, "token_gemm(tc): ldw=%d must be a multiple of 32 and >= %d", a->ldw, kpad);
-    static const bool v4 = [] { const char* e = getenv("NMRF_B200_GEMM_V"); return e && e[0] == '4'; }();
-    return v4 ? token_gemm_tc(*a, a->W_lo, ST(stream)) : token_gemm_tc5(*a, a->W_lo, ST(stream));
+    // NMRF_B200_GEMM_V selects an older schedule of the same arithmetic (4: single-role, 5: A operand in shared memory)
+    static const int ver = [] { const char* e = getenv("NMRF_B200_GEMM_V"); return (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 6; }();
+    if (ver == 4) return token_gemm_tc(*a, a->W_lo, ST(stream));
+    if (ver == 5) return token_gemm_tc5(*a, a->W_lo, ST(stream));
+    return token_gemm_tc6(*a, a->W_lo, ST(stream));
   }
   return token_gemm_simt(*a, ST(stream));
 }
@@ -93,7 +98,10 @@ int nmrf_set_attention_impl(int tensor_cores) {
   g_attn_tc.store(tensor_cores ? 1 : 0, std::memory_order_relaxed);
   return NMRF_OK;
 }
-int nmrf_debug_set_trace(void* dev_i64_4096) { return gemm_set_trace(reinterpret_cast<long long*>(dev_i64_4096)); }
+int nmrf_debug_set_trace(void* dev_i64_4096) {
+  gemm_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
+  return gemm6_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
+}
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
   return split_tf32(w, hi, lo, (long long)n, ST(stream));
 }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NMRF_B200_ABI_VERSION 2
+#define NMRF_B200_ABI_VERSION 3
 
 enum {
   NMRF_OK = 0,
@@ -65,8 +65,16 @@ typedef struct {
    * zero-padded to a multiple of 32 (ldw % 32 == 0); N % 16 == 0, N <= 512.  W_lo == NULL selects the
    * exact-fp32 FMA kernel. */
   const float* W_lo;
+  /* Optional (preferred by the tensor-core path): the same hi / lo weights as TILE IMAGES produced by
+   * nmrf_pack_weight_tiles -- [ceil(N/128)][ceil(K/32)] tiles of 128 rows x 32 fp32, each tile stored exactly as its
+   * SWIZZLE_128B shared-memory image (16 KB), so a tile is fetched with one TMA bulk copy (cp.async.bulk). */
+  const float* Wt_hi;
+  const float* Wt_lo;
 } nmrf_gemm_args;
 int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
+/* w [N,K] row-major (device) -> hi/lo tile images, K zero-padded to a multiple of 32, N to a multiple of 128:
+ * hi_tiles / lo_tiles must hold ceil(N/128)*ceil(K/32)*4096 floats each. */
+int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float* lo_tiles, void* stream);
 /* debug tooling: device buffer of 4096 int64 that CTA 0 of the tensor-core GEMM fills with clock64() stamps (NULL = off) */
 int nmrf_debug_set_trace(void* dev_i64_4096);
 /* hi = rna_tf32(w), lo = rna_tf32(w - hi), elementwise over n floats (device pointers) */

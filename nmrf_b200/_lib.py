@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class GemmArgs(Structure):
@@ -25,6 +25,7 @@ class GemmArgs(Structure):
         ("rows", c_int), ("N", c_int),
         ("act", c_int),
         ("W_lo", c_void_p),
+        ("Wt_hi", c_void_p), ("Wt_lo", c_void_p),
     ]
 
 
@@ -41,6 +42,7 @@ SIGNATURES = {
     "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
     "nmrf_set_attention_impl": [_I],
     "nmrf_debug_set_trace": [_P],
+    "nmrf_pack_weight_tiles": [_P, _I, _I, _P, _P, _P],
     "nmrf_cost_volume_topk": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, POINTER(SeedWeights), _P, _P, _P, _P],
     "nmrf_prop_gather": [_P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P],
     "nmrf_stripe_attention": [_P, _I, _I, _I, _I, _P, _P, _P, _P],

@@ -30,6 +30,7 @@ int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stre
 int gemm_set_trace(long long* dev_ptr);
 int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
+int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
                      float*, float*, int64_t*, cudaStream_t);
@@ -89,7 +90,7 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
     // NMRF_B200_GEMM_V selects an older schedule of the same arithmetic (4: single-role, 5: A operand in shared memory)
     static const int ver = [] { const char* e = getenv("NMRF_B200_GEMM_V"); return (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 6; }();
     if (ver == 4) return token_gemm_tc(*a, a->W_lo, ST(stream));
-    if (ver == 5) return token_gemm_tc5(*a, a->W_lo, ST(stream));
+    if (ver == 5 || !a->Wt_hi || !a->Wt_lo) return token_gemm_tc5(*a, a->W_lo, ST(stream));
     return token_gemm_tc6(*a, a->W_lo, ST(stream));
   }
   return token_gemm_simt(*a, ST(stream));
@@ -97,6 +98,9 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
 int nmrf_set_attention_impl(int tensor_cores) {
   g_attn_tc.store(tensor_cores ? 1 : 0, std::memory_order_relaxed);
   return NMRF_OK;
+}
+int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float* lo_tiles, void* stream) {
+  return pack_weight_tiles(w, N, K, hi_tiles, lo_tiles, ST(stream));
 }
 int nmrf_debug_set_trace(void* dev_i64_4096) {
   gemm_set_trace(reinterpret_cast<long long*>(dev_i64_4096));

@@ -36,6 +36,7 @@ constexpr int G6_DYN = 6 * G6_TILE + G6_EPI_WARPS * G6_STAGE_FLOATS * 4 + 1024; 
 
 struct G6Smem {
   uint64_t done[G6_NB];       // MMAs of the unit that used B slot s are complete (tcgen05.commit)
+  uint64_t full_b[G6_NB];     // the slot's two weight tiles have landed (TMA bulk copy, expect_tx 32 KB)
   uint64_t acc_full[G6_ACC];  // accumulator stage holds a finished tile (tcgen05.commit)
   uint64_t acc_empty[G6_ACC]; // epilogue has drained the stage (256 arrivals)
   uint32_t tmem_base;
@@ -67,6 +68,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
   long long* const tp = (blockIdx.x == 0 && (tid == 0 || tid == G6_MMA_WARP * 32 || tid == G6_EPI_WARP0 * 32)) ? g_trace6 : nullptr;
   const int Ktot = a.Kx + a.Ke;
   const int nkb = (Ktot + G6_BK - 1) / G6_BK;
+  const int nkb_w = nkb;                 // k-blocks per row of tiles in the weight images (K padded to 32)
   const int ntiles = n_rb * n_np;
   const bool ln = a.ln_gamma != nullptr;
   auto coord = [&](int t) {
@@ -83,7 +85,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   if (tid == 0) {
-    for (int i = 0; i < G6_NB; ++i) mbar_init(&sm.done[i], 1);
+    for (int i = 0; i < G6_NB; ++i) { mbar_init(&sm.done[i], 1); mbar_init(&sm.full_b[i], 1); }
     for (int i = 0; i < G6_ACC; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], G6_EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -97,17 +99,18 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
     // warp w may touch TMEM lanes 32*(w%4)..+32 only: thread -> row 32*(w%4)+lane, k-columns 16*(w/4)..+16 of the k-block
     const int a_row = (warp & 3) * 32 + lane, a_c0 = (warp >> 2) * 4;
     const uint32_t a_lane = ((uint32_t)((warp & 3) * 32)) << 16;
+    // weight tiles of local unit `ut` -> slot: ONE thread issues two 16 KB TMA bulk copies of the pre-swizzled tile images
     auto load_B = [&](const TileCoord& tc_, int ut, int slot) {
-      const int kb = ut / tc_.nnc, n0 = tc_.n_base + (ut % tc_.nnc) * G6_BN;
-      const int bn = min(G6_BN, a.N - n0);
-      for (int i = tid; i < bn * 8; i += G6_PROD) {
-        const int r = i >> 3, c = i & 7;
-        const size_t goff = (size_t)(n0 + r) * a.ldw + kb * G6_BK + c * 4;
-        const uint32_t so = swz(r, c);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_hi(slot) + so)), "l"(a.W + goff));
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(sB_lo(slot) + so)), "l"(W_lo + goff));
+      if (tid == 0) {
+        const int kb = ut / tc_.nnc, nchunk = tc_.n_base / G6_BN + (ut % tc_.nnc);
+        const size_t toff = ((size_t)nchunk * nkb_w + kb) * (G6_TILE / 4);
+        const uint32_t bar = smem_u32(&sm.full_b[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * G6_TILE) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sB_hi(slot))), "l"(a.Wt_hi + toff), "r"(G6_TILE), "r"(bar) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sB_lo(slot))), "l"(a.Wt_lo + toff), "r"(G6_TILE), "r"(bar) : "memory");
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     // LayerNorm statistics of a tile's 128 rows into buffer `par` (Kx == 128): one warp per 16 rows, coalesced
     auto tile_stats = [&](int row0, int par) {
@@ -183,9 +186,9 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
               const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float h = rna_tf32(vv[j]);
+                const float h = rna_tf32_fast(vv[j]);
                 hi[cc * 4 + j] = __float_as_uint(h);
-                lo[cc * 4 + j] = __float_as_uint(rna_tf32(vv[j] - h));
+                lo[cc * 4 + j] = __float_as_uint(rna_tf32_fast(vv[j] - h));
               }
             }
             const uint32_t ta = tmem + a_lane + (uint32_t)(G6_ACOL + (akb & 1) * 64 + a_c0 * 4);
@@ -199,10 +202,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
           ++akb;
         }
         trace(tp, unit * 8 + 3);
-        if (prefetch) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         trace(tp, unit * 8 + 4);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // cp.async'ed weights -> visible to the tensor core
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // A written with tcgen05.st -> ordered before the hand-off
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");
         trace(tp, unit * 8 + 5);
@@ -227,7 +227,8 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
         const int slot = unit % G6_NB;
         if (nc == 0) abuf = (akb++) & 1;
         trace(tp, 2048 + unit * 4 + 0);
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");      // A of this unit is in TMEM
+        mbar_wait(&sm.full_b[slot], (unit / G6_NB) & 1);                                  // B tiles have landed
         trace(tp, 2048 + unit * 4 + 1);
         if (lane == 0) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -312,6 +313,34 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
 }
 
 }  // namespace
+
+namespace {
+// one thread per destination float of the tile images
+__global__ void pack_weight_tiles_kernel(const float* __restrict__ w, int N, int K, int nkb, long long total,
+                                         float* __restrict__ hi, float* __restrict__ lo) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int within = (int)(i % 4096);               // float index inside the 16 KB tile image
+  const long long tile = i / 4096;
+  const int kb = (int)(tile % nkb), nc = (int)(tile / nkb);
+  const int r = within >> 5, pchunk = (within & 31) >> 2, e = within & 3;
+  const int c = pchunk ^ (r & 7);                   // logical 16-byte chunk stored at this physical position
+  const int n = nc * 128 + r, k = kb * 32 + c * 4 + e;
+  const float x = (n < N && k < K) ? w[(size_t)n * K + k] : 0.f;
+  const float h = tc::rna_tf32(x);
+  hi[i] = h;
+  lo[i] = tc::rna_tf32(x - h);
+}
+}  // namespace
+
+int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream) {
+  NMRF_REQUIRE(w && hi && lo && N > 0 && K > 0, "pack_weight_tiles: bad arguments");
+  const int nkb = (K + 31) / 32, nnc = (N + 127) / 128;
+  const long long total = (long long)nkb * nnc * 4096;
+  pack_weight_tiles_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, N, K, nkb, total, hi, lo);
+  count_launch();
+  return check_launch("pack_weight_tiles");
+}
 
 int gemm6_set_trace(long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_trace6, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? NMRF_OK : NMRF_ERR_CUDA;

@@ -15,6 +15,12 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
+// round-to-nearest (ties away) to TF32 with two integer ops.  cvt.rna.tf32.f32 compiles to 4 ALU instructions (it also
+// preserves inf/nan, which never occur here); the hi/lo split runs for every A element of every GEMM, so this matters.
+__device__ __forceinline__ float rna_tf32_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

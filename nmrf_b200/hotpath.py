@@ -150,15 +150,20 @@ class _Launches:
             Wp = W if Kp == K else torch.nn.functional.pad(W, (0, Kp - K))
             Wp = Wp.contiguous()
             hi, lo = torch.empty_like(Wp), torch.empty_like(Wp)
-            _lib.check(lib.nmrf_split_tf32(Wp.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wp.numel(),
-                                           torch.cuda.current_stream().cuda_stream), "split_tf32")
-            self._splits[key] = (hi, lo, W)
-        return self._splits[key][:2]
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(lib.nmrf_split_tf32(Wp.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wp.numel(), st), "split_tf32")
+            # tile images for the TMA bulk copies of the warp-specialised kernel
+            ntile = ((N + 127) // 128) * (Kp // 32)
+            thi, tlo = (torch.empty(ntile * 4096, device=W.device) for _ in range(2))
+            Wc = W.contiguous()
+            _lib.check(lib.nmrf_pack_weight_tiles(Wc.data_ptr(), N, K, thi.data_ptr(), tlo.data_ptr(), st), "pack_weight_tiles")
+            self._splits[key] = (hi, lo, thi, tlo, W, Wc)
+        return self._splits[key][:4]
 
     def gemm(self, what, X, W, Y, rows, N, *, Kx=None, E=None, Ke=0, ediv=1, ln=None, bias=None, R=None, act=ACT_NONE):
-        W_lo = None
+        W_lo = Wt_hi = Wt_lo = None
         if self.tensor_cores and N % 16 == 0 and N <= 512 and W.is_cuda:
-            W, W_lo = self.split(W)
+            W, W_lo, Wt_hi, Wt_lo = self.split(W)
         a = GemmArgs()
         a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), (Kx if Kx is not None else X.shape[1])
         a.E, a.lde, a.Ke, a.ediv = (E.data_ptr() if E is not None else None), (E.stride(0) if E is not None else 0), Ke, ediv
@@ -169,7 +174,9 @@ class _Launches:
         a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
         a.rows, a.N, a.act = rows, N, act
         a.W_lo = W_lo.data_ptr() if W_lo is not None else None
-        self.keep(a, X, W, W_lo, Y, E, ln, bias, R)
+        a.Wt_hi = Wt_hi.data_ptr() if Wt_hi is not None else None
+        a.Wt_lo = Wt_lo.data_ptr() if Wt_lo is not None else None
+        self.keep(a, X, W, W_lo, Wt_hi, Wt_lo, Y, E, ln, bias, R)
         # algorithmic work: 2*MAC flops; activations read+written once (weights are L2-resident, excluded)
         flops = 2.0 * rows * N * (a.Kx + Ke)
         nbytes = 4.0 * (rows * a.Kx + (rows // max(ediv, 1)) * Ke + rows * N * (2 if R is not None else 1))

@@ -44,7 +44,17 @@ def split_tf32(W):
     return hi, lo
 
 
-def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, W_lo=None):
+def pack_weight_tiles(W):
+    """(hi_tiles, lo_tiles): the weight as SWIZZLE_128B tile images for the TMA bulk copies (see nmrf_b200.h)"""
+    _chk(W, "W")
+    N, K = W.shape
+    ntile = ((N + 127) // 128) * ((K + 31) // 32)
+    hi, lo = (torch.empty(ntile * 4096, device=W.device) for _ in range(2))
+    _lib.check(lib.nmrf_pack_weight_tiles(W.data_ptr(), N, K, hi.data_ptr(), lo.data_ptr(), _stream()), "pack_weight_tiles")
+    return hi, lo
+
+
+def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, W_lo=None, Wt=None):
     """Y = act(concat(LN?(X), E[r // ediv]) @ W.T + bias) (+ R).  X [rows,Kx], E [*,Ke], W [N,>=Kx+Ke].
     With W_lo (and W = hi part, both from split_tf32) the tcgen05 3xTF32 kernel is used."""
     for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R), ("W_lo", W_lo)):
@@ -62,6 +72,7 @@ def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=N
     a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
     a.rows, a.N, a.act = rows, N, act
     a.W_lo = _p(W_lo)
+    a.Wt_hi, a.Wt_lo = (_p(Wt[0]), _p(Wt[1])) if Wt is not None else (None, None)
     _lib.check(lib.nmrf_token_gemm(ctypes.byref(a), _stream()), "token_gemm")
     return Y
 

@@ -38,7 +38,7 @@ def test_binding_matches_header():
 
 def test_helpers_work_without_a_gpu():
     from nmrf_b200 import _lib
-    assert _lib.lib.nmrf_abi_version() == _lib.ABI_VERSION == 2
+    assert _lib.lib.nmrf_abi_version() == _lib.ABI_VERSION == 3
     assert isinstance(_lib.launch_count(), int)
     # argument validation happens before any CUDA call: a bad GEMM is rejected with a message
     a = _lib.GemmArgs()
@@ -51,4 +51,4 @@ def test_struct_layout_matches_c():
     from nmrf_b200 import _lib
     assert ctypes.sizeof(_lib.SeedWeights) == 6 * 8
     # X,ldx,Kx | E,lde,Ke,ediv | g,b | W,ldw | bias | R,ldr | Y,ldy | rows,N,act
-    assert ctypes.sizeof(_lib.GemmArgs) == 128
+    assert ctypes.sizeof(_lib.GemmArgs) == 144

@@ -64,7 +64,8 @@ def test_token_gemm(ops, rows, Kx, Ke, ediv, N, ln, act, res, tc):
     if res:
         ref = ref + R.double()
     Wd, W_lo = (ops.split_tf32(cuda(W)) if tc else (cuda(W), None))
-    out = ops.token_gemm(cuda(X), Wd, E=cuda(E) if Ke else None, ediv=ediv, W_lo=W_lo,
+    Wt = ops.pack_weight_tiles(cuda(W)) if tc else None
+    out = ops.token_gemm(cuda(X), Wd, E=cuda(E) if Ke else None, ediv=ediv, W_lo=W_lo, Wt=Wt,
                          ln=(cuda(gam), cuda(bet)) if ln else None, bias=cuda(b), R=cuda(R) if res else None, act=act)
     assert rel_err(out, ref) <= (4e-6 if tc else 2e-6)
 
@@ -81,8 +82,10 @@ def test_token_gemm_tc_many_tiles_and_split_exactness(ops):
     X = torch.randn(rows, 128, generator=g)
     E = torch.randn(rows, 32, generator=g)
     ref = torch.cat([X, E], 1).double() @ W.double().T
-    out = ops.token_gemm(cuda(X), hi, E=cuda(E), W_lo=lo)
+    out = ops.token_gemm(cuda(X), hi, E=cuda(E), W_lo=lo, Wt=ops.pack_weight_tiles(cuda(W)))
     assert rel_err(out, ref) <= 4e-6
+    out5 = ops.token_gemm(cuda(X), hi, E=cuda(E), W_lo=lo)          # without tile images: the smem-A schedule
+    assert rel_err(out5, ref) <= 4e-6
 
 
 def test_token_gemm_residual_in_place(ops):

@@ -17,10 +17,11 @@ for name, rows, Kx, Ke, N, ln, act, res in [("fc2", 34560, 512, 0, 128, False, 0
     E = torch.randn(rows, Ke, generator=g).to(dev) if Ke else None
     W = (torch.randn(N, Kx + Ke, generator=g) / (Kx + Ke) ** 0.5).to(dev)
     hi, lo = ops.split_tf32(W)
+    Wt = ops.pack_weight_tiles(W)
     b = torch.randn(N, generator=g).to(dev)
     gam, bet = torch.ones(Kx, device=dev), torch.zeros(Kx, device=dev)
     R = torch.randn(rows, N, generator=g).to(dev) if res else None
-    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, W_lo=lo)
+    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, W_lo=lo, Wt=Wt)
     for _ in range(3):
         ops.token_gemm(X, hi, **kw)
     tr = torch.zeros(4096, dtype=torch.int64, device=dev)

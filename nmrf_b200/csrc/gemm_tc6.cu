@@ -4,17 +4,26 @@
 // UMMAs of a unit whose tensor work is 768 cycles: every SS-mode tf32 UMMA (128x128x8) reads 4 KB of A and 4 KB of B from
 // shared memory, so the MMAs alone saturate the shared-memory pipe while the producers' st.shared / cp.async traffic
 // competes with them.  Here the producers write the LayerNorm'ed, concatenated, hi/lo-split A operand straight into
-// TMEM (tcgen05.st) and the UMMA takes A from TMEM: shared memory only carries the weight tiles (B).
+// TMEM (tcgen05.st) and the UMMA takes A from TMEM: shared memory carries the weight tiles (B) and the raw A ring.
 //
 //   warps 0-7   producers   thread = (row, half of the 32-wide k-block): warp w owns TMEM lane quarter w%4 and k-columns
-//                           16*(w/4)..+16; raw A values prefetched three k-blocks ahead, LayerNorm statistics of the next
-//                           tile computed early; A_hi / A_lo -> TMEM (tcgen05.st 32x32b.x16), weight tiles by cp.async
+//                           16*(w/4)..+16.  The raw A tile [128 x 32] of a k-block comes into a 4-deep swizzled smem ring by
+//                           COALESCED cp.async (8 lanes = one row's 128 B; a per-thread row gather costs 32 L1 wavefronts
+//                           per instruction); the ring streams ACROSS tiles, three k-blocks ahead.  Per k-block: LDS ->
+//                           LayerNorm -> hi/lo split in registers, THEN wait for the MMAs that still read the A buffer,
+//                           then tcgen05.st (A_hi / A_lo -> TMEM) and hand over to the MMA warp.
 //   warp  8     MMA issuer  per unit: 4 k-steps x {A_lo.B_hi, A_hi.B_lo, A_hi.B_hi}, A from TMEM, B from swizzled smem
-//   warps 9-16  epilogue    as v5 (TMEM -> registers -> smem transpose -> coalesced bias/activation/residual/store)
+//   warps 9-16  epilogue    TMEM -> registers -> smem transpose -> coalesced bias/activation/residual/store; while they
+//                           wait they also compute the LayerNorm statistics of the tile three ahead (the producers used
+//                           to stall ~10k cycles per tile on those loads)
+//   warp  17    TMA         one lane streams the pre-swizzled weight tile images (2 x 16 KB cp.async.bulk per unit) into a
+//                           3-slot ring, as soon as the MMAs that read a slot have completed
 //
 //   tile        128 rows x 128 output columns, unit = one k-block of 32; three accumulator stages (3 x 128 TMEM columns)
 //               so the epilogue of a tile overlaps the MMAs of the next two; A tiles double buffered (2 x 64 columns).
 //               TMEM map: [0,384) accumulators, [384,512) A: buffer b at 384 + 64 b, hi at +0, lo at +32.
+//   waiting     one lane per warp polls an mbarrier, the others park at __syncwarp (tc_common.cuh: mbar_wait_warp):
+//               32-lane spins were a third of all issued instructions and clogged the MIO queue.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -22,32 +31,36 @@ namespace nmrf {
 namespace {
 using namespace tc;
 
-constexpr int G6_BM = 128, G6_BN = 128, G6_BK = 32, G6_NPASS = 128, G6_NB = 3, G6_ACC = 3;
+constexpr int G6_BM = 128, G6_BN = 128, G6_BK = 32, G6_NB = 3, G6_ACC = 3;
 constexpr int G6_ACOL = G6_ACC * G6_BN;             // first TMEM column of the A buffers
 constexpr int G6_TILE = G6_BM * G6_BK * 4;          // 16 KB operand tile
 constexpr int G6_PROD = 256;                        // producer threads (warps 0-7)
 constexpr int G6_MMA_WARP = 8;
 constexpr int G6_EPI_WARP0 = 9, G6_EPI_WARPS = 8;
-constexpr int G6_BLOCK = (G6_EPI_WARP0 + G6_EPI_WARPS) * 32;   // 544
-constexpr int G6_STATS_BAR = 4;                     // named barrier of the producers (LayerNorm statistics hand-over)
-constexpr int G6_HANDOFF = G6_PROD + 32;            // named-barrier population: producers arrive, MMA warp syncs
+constexpr int G6_TMA_WARP = G6_EPI_WARP0 + G6_EPI_WARPS;       // 17
+constexpr int G6_BLOCK = (G6_TMA_WARP + 1) * 32;               // 576
+constexpr int G6_HANDOFF = G6_PROD + 32;            // named barriers 1..3: producers arrive, MMA warp syncs
+constexpr int G6_RAW_BAR = 5;                       // named barrier of the producers: raw tile visible / consumed
 constexpr int G6_STAGE_FLOATS = 32 * 36;            // per-epilogue-warp transpose tile
-constexpr int G6_DYN = 6 * G6_TILE + G6_EPI_WARPS * G6_STAGE_FLOATS * 4 + 1024;   // B_hi[3] B_lo[3] + epilogue staging
+constexpr int G6_RAW = 4;                           // raw-A ring depth (k-blocks)
+constexpr int G6_STATS = 4;                         // LayerNorm statistics buffers (tiles in flight: 3 ahead)
+constexpr int G6_DYN = (6 + G6_RAW) * G6_TILE + G6_EPI_WARPS * G6_STAGE_FLOATS * 4 + 1024;   // B_hi[3] B_lo[3] raw[4] + epilogue staging
 
 struct G6Smem {
   uint64_t done[G6_NB];       // MMAs of the unit that used B slot s are complete (tcgen05.commit)
   uint64_t full_b[G6_NB];     // the slot's two weight tiles have landed (TMA bulk copy, expect_tx 32 KB)
   uint64_t acc_full[G6_ACC];  // accumulator stage holds a finished tile (tcgen05.commit)
   uint64_t acc_empty[G6_ACC]; // epilogue has drained the stage (256 arrivals)
+  uint64_t stats_full[G6_STATS];          // LayerNorm statistics of a tile are in mean/rstd (8 arrivals: one per epilogue warp)
   uint32_t tmem_base;
-  float mean[2][G6_BM], rstd[2][G6_BM];   // LayerNorm statistics, double buffered across tiles
+  float mean[G6_STATS][G6_BM], rstd[G6_STATS][G6_BM];
+  alignas(16) float gamma[128];           // LayerNorm affine (Kx == 128), staged once; read as float4
+  alignas(16) float beta[128];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-
-struct TileCoord { int row0, n_base, npass, nnc; };
 
 // optional cycle trace of CTA 0 (debug tooling: nmrf_debug_set_trace); slot layout documented in tools/gemm_trace.py
 __device__ long long* g_trace6 = nullptr;
@@ -55,30 +68,60 @@ __device__ __forceinline__ void trace(long long* tp, int idx) {
   if (tp && idx < 4096) tp[idx] = clock64();
 }
 
+// LayerNorm statistics of 16 rows of a tile (Kx == 128) by one warp: 8 lanes per row (16 floats each, every load
+// instruction covers four rows' contiguous 128 B), four rows per pass, all 16 loads of a lane in flight at once, two
+// 3-stage shuffle reductions (two-pass variance, like the reference's LayerNorm).  A whole-warp-per-row version chained
+// 160 dependent shuffles and took ~11k cycles per call.  Out of line: the warp-specialised kernel's instruction footprint
+// matters (four roles share the instruction cache).
+__device__ __noinline__ void tile_stats6(const float* __restrict__ X, int ldx, int rows, int row0, int e, float* mean, float* rstd) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  float4 v[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + e * 16 + i * 4 + g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) v[i][j] = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + j * 32 + sub * 4);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += (v[i][j].x + v[i][j].y) + (v[i][j].z + v[i][j].w);
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mu = s * (1.f / 128.f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dx = v[i][j].x - mu, dy = v[i][j].y - mu, dz = v[i][j].z - mu, dw = v[i][j].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+    if (sub == 0) { const int lr = e * 16 + i * 4 + g; mean[lr] = mu; rstd[lr] = 1.f / sqrtf(q * (1.f / 128.f) + 1e-5f); }
+  }
+}
+
+// tile t -> (row block, 128-column chunk): column-chunk-major, so concurrently running CTAs share a weight chunk (L2)
+template <int ACT, bool LN>
 __global__ void __launch_bounds__(G6_BLOCK, 1)
-token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int n_rb, int n_np) {
+token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   __shared__ G6Smem sm;
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
   auto sB_hi = [&](int i) { return base + i * G6_TILE; };
   auto sB_lo = [&](int i) { return base + (3 + i) * G6_TILE; };
-  float* stage_base = reinterpret_cast<float*>(base + 6 * G6_TILE);
+  auto sRaw = [&](int i) { return base + (6 + i) * G6_TILE; };
+  float* stage_base = reinterpret_cast<float*>(base + (6 + G6_RAW) * G6_TILE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long* const tp = (blockIdx.x == 0 && (tid == 0 || tid == G6_MMA_WARP * 32 || tid == G6_EPI_WARP0 * 32)) ? g_trace6 : nullptr;
+  long long* const tp2 = (blockIdx.x == 0 && tid == 32) ? g_trace6 : nullptr;
   const int Ktot = a.Kx + a.Ke;
   const int nkb = (Ktot + G6_BK - 1) / G6_BK;
-  const int nkb_w = nkb;                 // k-blocks per row of tiles in the weight images (K padded to 32)
-  const int ntiles = n_rb * n_np;
-  const bool ln = a.ln_gamma != nullptr;
-  auto coord = [&](int t) {
-    TileCoord c;
-    c.row0 = (t % n_rb) * G6_BM;           // pass-major order: with a persistent stride of gridDim.x every CTA gets the same
-    c.n_base = (t / n_rb) * G6_NPASS;      // mix of wide (256-column) and narrow passes
-    c.npass = min(G6_NPASS, a.N - c.n_base);
-    c.nnc = (c.npass + G6_BN - 1) / G6_BN;
-    return c;
-  };
+  const int ntiles = n_rb * n_nc;
+  const int tstep = gridDim.x;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
@@ -87,8 +130,10 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
   if (tid == 0) {
     for (int i = 0; i < G6_NB; ++i) { mbar_init(&sm.done[i], 1); mbar_init(&sm.full_b[i], 1); }
     for (int i = 0; i < G6_ACC; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], G6_EPI_WARPS * 32); }
+    for (int i = 0; i < G6_STATS; ++i) mbar_init(&sm.stats_full[i], G6_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (LN && tid < 128) { sm.gamma[tid] = a.ln_gamma[tid]; sm.beta[tid] = a.ln_beta[tid]; }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -99,144 +144,128 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
     // warp w may touch TMEM lanes 32*(w%4)..+32 only: thread -> row 32*(w%4)+lane, k-columns 16*(w/4)..+16 of the k-block
     const int a_row = (warp & 3) * 32 + lane, a_c0 = (warp >> 2) * 4;
     const uint32_t a_lane = ((uint32_t)((warp & 3) * 32)) << 16;
-    // weight tiles of local unit `ut` -> slot: ONE thread issues two 16 KB TMA bulk copies of the pre-swizzled tile images
-    auto load_B = [&](const TileCoord& tc_, int ut, int slot) {
-      if (tid == 0) {
-        const int kb = ut / tc_.nnc, nchunk = tc_.n_base / G6_BN + (ut % tc_.nnc);
-        const size_t toff = ((size_t)nchunk * nkb_w + kb) * (G6_TILE / 4);
-        const uint32_t bar = smem_u32(&sm.full_b[slot]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * G6_TILE) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sB_hi(slot))), "l"(a.Wt_hi + toff), "r"(G6_TILE), "r"(bar) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sB_lo(slot))), "l"(a.Wt_lo + toff), "r"(G6_TILE), "r"(bar) : "memory");
+    // Raw-A ring, streaming across tiles.  fetch(): k-block f_kb of tile f_t -> stage `stage`: 1024 16-byte chunks, 4 per
+    // thread, lanes 8j..8j+7 cover one row's 128 B; chunk c of row r lands at position c ^ (r & 7) (conflict-free row reads
+    // later); rows / columns outside the problem are zero-filled (src-size 0).  Past the last tile: an empty group, so the
+    // wait_group accounting stays uniform (one group per unit).
+    const int f_c = tid & 7, f_r = tid >> 3;
+    int f_t = blockIdx.x, f_kb = 0;
+    const float* f_x[4];       // this thread's four source rows of the fetch cursor's tile (X part, E part), refreshed per tile:
+    const float* f_e[4];       // the index arithmetic (a modulo, a division by ediv) stays out of the per-unit path
+    uint32_t f_ok = 0;
+    auto fetch_tile = [&]() {
+      const int row0 = (f_t % n_rb) * G6_BM;
+      f_ok = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int grow = row0 + f_r + 32 * j;
+        const bool ok = grow < a.rows;
+        f_ok |= (ok ? 1u : 0u) << j;
+        const int gr = ok ? grow : 0;
+        f_x[j] = a.X + (size_t)gr * a.ldx + f_c * 4;
+        f_e[j] = a.E ? a.E + (size_t)(gr / a.ediv) * a.lde + f_c * 4 - a.Kx : a.X;
       }
     };
-    // LayerNorm statistics of a tile's 128 rows into buffer `par` (Kx == 128): one warp per 16 rows, coalesced
-    auto tile_stats = [&](int row0, int par) {
-      for (int i = 0; i < G6_BM / 8; ++i) {
-        const int lr = warp * (G6_BM / 8) + i, r = row0 + lr;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < a.rows) v = *reinterpret_cast<const float4*>(a.X + (size_t)r * a.ldx + lane * 4);
-        const float mu = warp_sum(v.x + v.y + v.z + v.w) * (1.f / 128.f);
-        const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
-        const float var = warp_sum(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 128.f);
-        if (lane == 0) { sm.mean[par][lr] = mu; sm.rstd[par][lr] = 1.f / sqrtf(var + 1e-5f); }
+    if (f_t < ntiles) fetch_tile();
+    auto fetch_next = [&](uint32_t stage) {
+      if (f_t < ntiles) {
+        const uint32_t dst = smem_u32(sRaw(stage));
+        const int k0 = f_kb * G6_BK;
+        const bool in_x = k0 + f_c * 4 < a.Kx, in_k = k0 + f_c * 4 < Ktot;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = in_k && ((f_ok >> j) & 1u);
+          const float* src = (in_x ? f_x[j] : f_e[j]) + k0;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(f_r + 32 * j, f_c)), "l"(ok ? src : a.X), "r"(ok ? 16 : 0));
+        }
+        if (++f_kb == nkb) { f_kb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
       }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    uint32_t unit = 0;
-    uint32_t akb = 0;          // k-blocks produced so far by this CTA: A buffer = akb & 1 (alternates ACROSS tiles too, so the
-                               // buffer being rewritten was last read two k-blocks -- at least two units -- ago)
-    int par = 0;
-    if ((int)blockIdx.x < ntiles) {
-      load_B(coord(blockIdx.x), 0, 0);
-      if (ln) tile_stats(coord(blockIdx.x).row0, 0);
-    }
-    asm volatile("bar.sync %0, %1;" ::"r"(G6_STATS_BAR), "r"(G6_PROD) : "memory");
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const TileCoord tc_ = coord(t);
-      const bool has_next = t + (int)gridDim.x < ntiles;
-      const int g_row = tc_.row0 + a_row;
-      const bool row_ok = g_row < a.rows;
-      const float* xrow = a.X + (size_t)(row_ok ? g_row : 0) * a.ldx;
-      const float* erow = a.E ? a.E + (size_t)((row_ok ? g_row : 0) / a.ediv) * a.lde : nullptr;
-      const float mean = ln ? sm.mean[par][a_row] : 0.f, rstd = ln ? sm.rstd[par][a_row] : 1.f;
-      float4 ar0[4], ar1[4], ar2[4];          // raw A values of three k-blocks in flight (round-robin, no register moves)
-      auto fetch_A = [&](int kb, float4 (&dst)[4]) {
+    fetch_next(0); fetch_next(1); fetch_next(2);
+    uint32_t unit = 0;         // == k-blocks produced so far by this CTA: ring stage unit % 4, A buffer unit & 1, B slot unit % 3
+    int it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
+      const int row0 = (t % n_rb) * G6_BM;
+      const bool row_ok = row0 + a_row < a.rows;
+      float mean = 0.f, rstd = 1.f;
+      if (LN) {
+        mbar_wait_warp(&sm.stats_full[it % G6_STATS], (it / G6_STATS) & 1);
+        mean = sm.mean[it % G6_STATS][a_row]; rstd = sm.rstd[it % G6_STATS][a_row];
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++unit) {
+        const int slot = unit % G6_NB;
+        trace(tp, unit * 8 + 0);
+        // this k-block's raw tile has landed for every producer thread (own copies: wait_group; others': barrier)
+        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(G6_RAW_BAR), "r"(G6_PROD) : "memory");
+        trace(tp2, 1024 + unit * 8 + 0);
+        const uint8_t* raw = sRaw(unit % G6_RAW);
+        uint32_t hi[16], lo[16];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          const int kk = kb * G6_BK + (a_c0 + cc) * 4;
-          const float* p = (kk < a.Kx) ? xrow + kk : erow + (kk - a.Kx);
-          dst[cc] = (row_ok && kk < Ktot) ? *reinterpret_cast<const float4*>(p) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const int c = a_c0 + cc;
+          const int kk = kb * G6_BK + c * 4;
+          float4 v = *reinterpret_cast<const float4*>(raw + swz(a_row, c));
+          if (LN && row_ok && kk < a.Kx) {
+            const float4 g = *reinterpret_cast<const float4*>(sm.gamma + kk);
+            const float4 b = *reinterpret_cast<const float4*>(sm.beta + kk);
+            v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
+            v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
+          }
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float h = rna_tf32_fast(vv[j]);
+            hi[cc * 4 + j] = __float_as_uint(h);
+            lo[cc * 4 + j] = __float_as_uint(rna_tf32_fast(vv[j] - h));
+          }
         }
-      };
-      fetch_A(0, ar0);
-      fetch_A(1, ar1);
-      fetch_A(2, ar2);
-      const int upt = nkb * tc_.nnc;
-      const int stats_at = upt > 3 ? upt - 3 : 0;            // next tile's statistics go out while the last units are produced
-      for (int ut = 0; ut < upt; ++ut, ++unit) {
-        const int kb = ut / tc_.nnc, nc = ut - kb * tc_.nnc;
-        const int slot = unit % G6_NB;
-        // MMAs of unit-2 (and, cumulatively, all earlier ones) are complete: frees B slot (unit+1)%3 and the A buffer of
-        // k-block akb-2.  unit-2 is the newest unit whose barrier phase is unambiguous (its slot is next used by unit+1).
-        trace(tp, unit * 8 + 0);
-        if (unit >= 2) mbar_wait(&sm.done[(unit - 2) % G6_NB], ((unit - 2) / G6_NB) & 1);
+        trace(tp2, 1024 + unit * 8 + 1);
+        // the MMAs of unit-2 (and, cumulatively, all earlier ones) are complete: A buffer unit & 1 may be overwritten
+        if (unit >= 2) {
+          mbar_wait_warp(&sm.done[(unit - 2) % G6_NB], ((unit - 2) / G6_NB) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
         trace(tp, unit * 8 + 1);
-        const bool prefetch = (ut + 1 < upt) || has_next;
-        if (prefetch) {
-          if (ut + 1 < upt) load_B(tc_, ut + 1, (unit + 1) % G6_NB);
-          else load_B(coord(t + gridDim.x), 0, (unit + 1) % G6_NB);
-        }
-        trace(tp, unit * 8 + 2);
-        if (ut == stats_at && has_next && ln) tile_stats(coord(t + gridDim.x).row0, par ^ 1);
-        if (nc == 0) {
-          auto produce = [&](float4 (&buf)[4]) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-              const int kk = kb * G6_BK + (a_c0 + cc) * 4;
-              float4 v = buf[cc];
-              if (ln && row_ok && kk < a.Kx) {
-                const float4 g = *reinterpret_cast<const float4*>(a.ln_gamma + kk);
-                const float4 b = *reinterpret_cast<const float4*>(a.ln_beta + kk);
-                v.x = (v.x - mean) * rstd * g.x + b.x; v.y = (v.y - mean) * rstd * g.y + b.y;
-                v.z = (v.z - mean) * rstd * g.z + b.z; v.w = (v.w - mean) * rstd * g.w + b.w;
-              }
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float h = rna_tf32_fast(vv[j]);
-                hi[cc * 4 + j] = __float_as_uint(h);
-                lo[cc * 4 + j] = __float_as_uint(rna_tf32_fast(vv[j] - h));
-              }
-            }
-            const uint32_t ta = tmem + a_lane + (uint32_t)(G6_ACOL + (akb & 1) * 64 + a_c0 * 4);
-            tmem_st16(ta, hi);
-            tmem_st16(ta + 32, lo);
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            fetch_A(kb + 3, buf);
-          };
-          const int which = kb % 3;
-          if (which == 0) produce(ar0); else if (which == 1) produce(ar1); else produce(ar2);
-          ++akb;
-        }
-        trace(tp, unit * 8 + 3);
-        trace(tp, unit * 8 + 4);
+        trace(tp2, 1024 + unit * 8 + 2);
+        const uint32_t ta = tmem + a_lane + (uint32_t)(G6_ACOL + (unit & 1) * 64 + a_c0 * 4);
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32, lo);
+        trace(tp2, 1024 + unit * 8 + 3);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  // A written with tcgen05.st -> ordered before the hand-off
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");
-        trace(tp, unit * 8 + 5);
+        trace(tp, unit * 8 + 2);
+        trace(tp2, 1024 + unit * 8 + 4);
+        // re-arm the ring three k-blocks ahead: that stage was consumed (by every producer) one unit ago, before the
+        // barrier above
+        fetch_next((unit + 3) % G6_RAW);
+        trace(tp2, 1024 + unit * 8 + 5);
       }
-      // the next tile's statistics (written by other warps) become visible to every producer
-      asm volatile("bar.sync %0, %1;" ::"r"(G6_STATS_BAR), "r"(G6_PROD) : "memory");
-      par ^= 1;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == G6_MMA_WARP) {
     // =============================================== MMA issuer ===============================================
     uint32_t unit = 0;
-    uint32_t akb = 0, abuf = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const TileCoord tc_ = coord(t);
+    for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
+      const int n_base = (t / n_rb) * G6_BN;
       const int as = it % G6_ACC;
-      if (it >= G6_ACC) mbar_wait(&sm.acc_empty[as], ((it / G6_ACC) - 1) & 1);   // epilogue of tile it-3 has drained the stage
+      if (it >= G6_ACC) mbar_wait_warp(&sm.acc_empty[as], ((it / G6_ACC) - 1) & 1, 32);   // epilogue of tile it-3 has drained the stage
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int upt = nkb * tc_.nnc;
-      for (int ut = 0; ut < upt; ++ut, ++unit) {
-        const int kb = ut / tc_.nnc, nc = ut - kb * tc_.nnc;
+      const uint32_t idesc = make_idesc(min(G6_BN, a.N - n_base));
+      for (int kb = 0; kb < nkb; ++kb, ++unit) {
         const int slot = unit % G6_NB;
-        if (nc == 0) abuf = (akb++) & 1;
         trace(tp, 2048 + unit * 4 + 0);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");      // A of this unit is in TMEM
-        mbar_wait(&sm.full_b[slot], (unit / G6_NB) & 1);                                  // B tiles have landed
+        mbar_wait_warp(&sm.full_b[slot], (unit / G6_NB) & 1);                             // B tiles have landed
         trace(tp, 2048 + unit * 4 + 1);
         if (lane == 0) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const int bn = min(G6_BN, tc_.npass - nc * G6_BN);
-          const uint32_t idesc = make_idesc(bn);
           const uint64_t dBh = make_desc(smem_u32(sB_hi(slot))), dBl = make_desc(smem_u32(sB_lo(slot)));
           const uint32_t d = tmem + (uint32_t)(as * G6_BN);
-          const uint32_t tAh = tmem + (uint32_t)(G6_ACOL + abuf * 64), tAl = tAh + 32;
+          const uint32_t tAh = tmem + (uint32_t)(G6_ACOL + (unit & 1) * 64), tAl = tAh + 32;
 #pragma unroll
           for (int ks = 0; ks < G6_BK / 8; ++ks) {
             const uint64_t adv = (uint64_t)(ks * 2);               // B: +32 bytes inside the swizzle row; A: +8 TMEM columns
@@ -245,10 +274,29 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
             umma_tf32_ta(d, tAh + ks * 8, dBh + adv, idesc, 1u);
           }
           umma_commit(&sm.done[slot]);
-          if (ut == upt - 1) umma_commit(&sm.acc_full[as]);
+          if (kb == nkb - 1) umma_commit(&sm.acc_full[as]);
         }
         __syncwarp();
         trace(tp, 2048 + unit * 4 + 2);
+      }
+    }
+  } else if (warp == G6_TMA_WARP) {
+    // =============================================== weight tiles (TMA) ===============================================
+    if (lane == 0) {
+      uint32_t unit = 0;
+      for (int t = blockIdx.x; t < ntiles; t += tstep) {
+        const int nchunk = t / n_rb;
+        for (int kb = 0; kb < nkb; ++kb, ++unit) {
+          const int slot = unit % G6_NB;
+          if (unit >= G6_NB) mbar_wait(&sm.done[slot], ((unit - G6_NB) / G6_NB) & 1);   // MMAs that read this slot are complete
+          const size_t toff = ((size_t)nchunk * nkb + kb) * (G6_TILE / 4);
+          const uint32_t bar = smem_u32(&sm.full_b[slot]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * G6_TILE) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(sB_hi(slot))), "l"(a.Wt_hi + toff), "r"(G6_TILE), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(sB_lo(slot))), "l"(a.Wt_lo + toff), "r"(G6_TILE), "r"(bar) : "memory");
+        }
       }
     }
   } else {
@@ -258,15 +306,27 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
     const int half = e >> 2;                   // two warps per quarter: even / odd 32-column chunks
     float* stage = stage_base + e * G6_STAGE_FLOATS;
     const int srow = lane >> 3, scol = (lane & 7) * 4;
+    // LayerNorm statistics of local tile j -> buffer j % 4 (16 rows per warp), three tiles ahead of the drain
+    auto stats = [&](int j) {
+      const int tj = blockIdx.x + j * tstep;
+      if (tj < ntiles) {
+        tile_stats6(a.X, a.ldx, a.rows, (tj % n_rb) * G6_BM, e, sm.mean[j % G6_STATS], sm.rstd[j % G6_STATS]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.stats_full[j % G6_STATS]);
+      }
+    };
+    if (LN) { stats(0); stats(1); stats(2); }
     int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
-      const TileCoord tc_ = coord(t);
+    for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
+      const int row0 = (t % n_rb) * G6_BM, n_base = (t / n_rb) * G6_BN;
       const int as = it % G6_ACC;
+      // buffer (it+3) % 4 last held tile it-1, whose statistics the producers read before its MMAs, which this warp drained
+      if (LN) stats(it + 3);
       trace(tp, 3584 + it * 4 + 0);
-      mbar_wait(&sm.acc_full[as], (it / G6_ACC) & 1);
+      mbar_wait_warp(&sm.acc_full[as], (it / G6_ACC) & 1, 64);
       trace(tp, 3584 + it * 4 + 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int nchunks = (tc_.npass + 31) / 32;
+      const int nchunks = (min(G6_BN, a.N - n_base) + 31) / 32;
       for (int ch = half; ch < nchunks; ch += 2) {
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G6_BN + ch * 32), v);
@@ -274,25 +334,25 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         __syncwarp();
-        const int n = tc_.n_base + ch * 32 + scol;
+        const int n = n_base + ch * 32 + scol;
         if (n < a.N) {
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.bias) b = *reinterpret_cast<const float4*>(a.bias + n);
           float4 rr[8];                         // residual first (R may alias Y: read-before-write by the same thread)
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
-            const int r = tc_.row0 + q * 32 + i8 * 4 + srow;
+            const int r = row0 + q * 32 + i8 * 4 + srow;
             rr[i8] = (a.R && r < a.rows) ? __ldcg(reinterpret_cast<const float4*>(a.R + (size_t)r * a.ldr + n))
                                          : make_float4(0.f, 0.f, 0.f, 0.f);
           }
 #pragma unroll
           for (int i8 = 0; i8 < 8; ++i8) {
             const int lr = i8 * 4 + srow;
-            const int r = tc_.row0 + q * 32 + lr;
+            const int r = row0 + q * 32 + lr;
             if (r < a.rows) {
               float4 o = *reinterpret_cast<const float4*>(stage + lr * 36 + scol);
-              o.x = act_fast(o.x + b.x, a.act) + rr[i8].x; o.y = act_fast(o.y + b.y, a.act) + rr[i8].y;
-              o.z = act_fast(o.z + b.z, a.act) + rr[i8].z; o.w = act_fast(o.w + b.w, a.act) + rr[i8].w;
+              o.x = act_fast(o.x + b.x, ACT) + rr[i8].x; o.y = act_fast(o.y + b.y, ACT) + rr[i8].y;
+              o.z = act_fast(o.z + b.z, ACT) + rr[i8].z; o.w = act_fast(o.w + b.w, ACT) + rr[i8].w;
               *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
             }
           }
@@ -346,21 +406,40 @@ int gemm6_set_trace(long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_trace6, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? NMRF_OK : NMRF_ERR_CUDA;
 }
 
+namespace {
+template <int ACT, bool LN>
+void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t stream) {
+  static bool configured = false;     // per instantiation
+  if (!configured) {
+    cudaFuncSetAttribute(token_gemm_tc6_kernel<ACT, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G6_DYN);
+    configured = true;
+  }
+  token_gemm_tc6_kernel<ACT, LN><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc);
+}
+}  // namespace
+
 int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream) {
   static int num_sms = 0;
-  static bool configured = false;
-  if (!configured) {
+  if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(token_gemm_tc6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G6_DYN);
-    configured = true;
   }
   const int n_rb = (a.rows + G6_BM - 1) / G6_BM;
-  const int n_np = (a.N + G6_NPASS - 1) / G6_NPASS;
-  const int ntiles = n_rb * n_np;
+  const int n_nc = (a.N + G6_BN - 1) / G6_BN;
+  const int ntiles = n_rb * n_nc;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  token_gemm_tc6_kernel<<<grid, G6_BLOCK, G6_DYN, stream>>>(a, W_lo, n_rb, n_np);
+  const bool ln = a.ln_gamma != nullptr;
+  // activation and LayerNorm are compile-time: each instantiation carries only its own epilogue / statistics code
+  switch (a.act * 2 + (ln ? 1 : 0)) {
+    case 0: launch6<0, false>(a, n_rb, n_nc, grid, stream); break;
+    case 1: launch6<0, true>(a, n_rb, n_nc, grid, stream); break;
+    case 2: launch6<1, false>(a, n_rb, n_nc, grid, stream); break;
+    case 3: launch6<1, true>(a, n_rb, n_nc, grid, stream); break;
+    case 4: launch6<2, false>(a, n_rb, n_nc, grid, stream); break;
+    case 5: launch6<2, true>(a, n_rb, n_nc, grid, stream); break;
+    default: set_error("token_gemm: unknown activation %d", a.act); return NMRF_ERR_BAD_ARG;
+  }
   count_launch();
   return check_launch("token_gemm_tc6");
 }

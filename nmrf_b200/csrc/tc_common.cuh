@@ -25,18 +25,38 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
 // bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  uint32_t done = 0;
-  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return;
-  }
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin)
+    if (mbar_try(addr, parity)) return;
   __trap();
+}
+// Whole-warp wait (every lane must call it, converged): ONE lane polls, the rest park at the warp barrier.  32 lanes x many
+// warps spinning on try_wait flood the MIO queue the producers' LDS / LDGSTS / STTM go through (a third of all issued
+// instructions of the first warp-specialised GEMM were this spin).  `sleep_ns` > 0 backs off between polls: for waits
+// with slack (an epilogue waiting for a whole tile of MMAs).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 0) {
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t addr = smem_u32(bar);
+    bool ok = false;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < SPIN_LIMIT && !ok; ++spin) {
+      ok = mbar_try(addr, parity);
+      if (!ok && sleep_ns) __nanosleep(sleep_ns);
+    }
+    if (!ok) __trap();
+  }
+  __syncwarp();
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):

@@ -1,6 +1,6 @@
 """Cycle-level trace of CTA 0 of the warp-specialised tcgen05 GEMM (run under gpurun).
-Stamps (clock64): producer thread 0: unit*8 + {0 loop top, 1 after done-wait, 2 after B prefetch issue, 3 after A produce,
-4 after cp.async wait, 5 after hand-off}; MMA lane 0: 2048 + unit*4 + {0 before bar.sync, 1 after, 2 after issue+commit};
+Stamps (clock64): producer thread 32: 1024 + unit*8 + {0 raw tile visible, 1 split done, 2 A buffer free (done-wait),
+3 tcgen05.st issued, 4 handed off, 5 ring re-armed}; MMA lane 0: 2048 + unit*4 + {0 before bar.sync, 1 after, 2 after issue+commit};
 epilogue warp 0 lane 0: 3584 + tile*4 + {0 before acc_full wait, 1 after, 2 after drain}."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -31,14 +31,16 @@ for name, rows, Kx, Ke, N, ln, act, res in [("fc2", 34560, 512, 0, 128, False, 0
     _lib.check(_lib.lib.nmrf_debug_set_trace(None), "set_trace")
     t = tr.cpu().tolist()
     t0 = min(v for v in t if v > 0)
-    prod = [[(t[u * 8 + k] - t0) if t[u * 8 + k] else None for k in range(6)] for u in range(40) if t[u * 8]]
+    prod = [[(t[u * 8 + k] - t0) if t[u * 8 + k] else None for k in range(3)] for u in range(40) if t[u * 8]]
     mma = [[(t[2048 + u * 4 + k] - t0) if t[2048 + u * 4 + k] else None for k in range(3)] for u in range(40) if t[2048 + u * 4]]
     epi = [[(t[3584 + i * 4 + k] - t0) if t[3584 + i * 4 + k] else None for k in range(3)] for i in range(8) if t[3584 + i * 4]]
     out[name] = dict(us=s.elapsed_time(e) * 1e3, producer=prod, mma=mma, epilogue=epi)
     print(name, f"{s.elapsed_time(e)*1e3:.1f} us")
-    print("  producer (top, +wait, +Bissue, +Aprod, +cpwait, +handoff):")
-    for u, r in enumerate(prod[:24]):
-        print("   u%02d" % u, r[0], [r[k] - r[k - 1] for k in range(1, 6)])
+    p2 = [[(t[1024 + u * 8 + k] - t0) if t[1024 + u * 8 + k] else None for k in range(6)] for u in range(24) if t[1024 + u * 8]]
+    print("  producer thread 32: raw tile ready at | LDS+LN+split, done-wait, STTM issue, wait::st+handoff, ring re-arm | next unit's raw wait")
+    for u, r in enumerate(p2[:12]):
+        nxt = (p2[u + 1][0] - r[5]) if u + 1 < len(p2) else None
+        print("   u%02d" % u, r[0], "|", r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], "|", nxt)
     print("  mma (before sync, wait, issue):")
     for u, r in enumerate(mma[:24]):
         print("   u%02d" % u, r[0], r[1] - r[0], r[2] - r[1])

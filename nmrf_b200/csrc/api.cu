@@ -40,6 +40,8 @@ int proposal_attention(const float*, int, int, float*, cudaStream_t);
 int window_attention(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int stripe_attention(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int stripe_attention_tc(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+bool window_attention_mma_supported(int K, int ws);
+int window_attention_mma(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int,
                     int, int, float, float*, float*, cudaStream_t);
 int zero_pad_rows(float*, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -146,6 +148,12 @@ int nmrf_proposal_attention(const float* qkv, int P, int K, float* out, void* st
 }
 int nmrf_window_attention(const float* qkv, const float* table, int B, int Hp, int Wp, int K, int ws, int shift,
                           int self_edge_mask, float* out, void* stream) {
+  if (attn_on_tensor_cores() && window_attention_mma_supported(K, ws)) {
+    NMRF_REQUIRE(qkv && table && out, "window_attention: null pointer");
+    NMRF_REQUIRE(Hp % ws == 0 && Wp % ws == 0, "window_attention: grid %dx%d not a multiple of ws=%d", Hp, Wp, ws);
+    NMRF_REQUIRE(shift >= 0 && shift < ws, "window_attention: shift=%d", shift);
+    return window_attention_mma(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask, out, ST(stream));
+  }
   return window_attention(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask, out, ST(stream));
 }
 int nmrf_select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K, int Hp,

@@ -221,8 +221,8 @@ def test_proposal_attention(ops, P, K):
 
 @pytest.mark.parametrize("B,Hp,Wp,K,ws,shift,self_edge", [
     (1, 12, 18, 4, 6, 0, True), (1, 12, 18, 4, 6, 3, True), (2, 6, 12, 2, 6, 3, True),
-    (1, 8, 12, 1, 4, 0, False), (2, 8, 12, 1, 4, 2, False), (1, 16, 28, 1, 4, 2, False), (1, 6, 6, 3, 6, 3, True)])
-def test_window_attention(ops, B, Hp, Wp, K, ws, shift, self_edge):
+    (1, 8, 12, 1, 4, 0, False), (2, 8, 12, 1, 4, 2, False), (1, 16, 28, 1, 4, 2, False), (1, 6, 6, 3, 6, 3, True), (3, 18, 12, 4, 6, 3, True), (1, 36, 44, 1, 4, 2, True)])
+def test_window_attention(ops, attn_impl, B, Hp, Wp, K, ws, shift, self_edge):
     g = torch.Generator().manual_seed(Hp * Wp + shift)
     qkv = torch.randn(B, Hp, Wp, K, 384, generator=g)
     table = 0.5 * torch.randn((2 * ws - 1) ** 2, 384, generator=g)

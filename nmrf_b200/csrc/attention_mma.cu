@@ -22,6 +22,7 @@
 // 3xTF32: every product is  a_lo.b_hi + a_hi.b_lo + a_hi.b_hi  with round-to-nearest splits (see tc_common.cuh).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cstdlib>
 
 namespace nmrf {
 namespace {
@@ -35,10 +36,12 @@ struct WinMmaParams {
   int B, Hp, Wp, shift, self_edge, nwy, nwx, nwin;
 };
 
+// hi = x rounded to nearest tf32; lo = x - hi handed over unrounded: the tensor core reads only the upper 19 bits, and
+// truncating lo loses at most 2^-13 |lo| <= 2^-25 |x|
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
   const float h = rna_tf32_fast(x);
   hi = __float_as_uint(h);
-  lo = __float_as_uint(rna_tf32_fast(x - h));
+  lo = __float_as_uint(x - h);
 }
 __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -72,8 +75,8 @@ struct Geo {
   }
 };
 
-template <int WS, int K, int WPC>
-__global__ void __launch_bounds__(WPC * Geo<WS, K>::NB * 32, (WPC * Geo<WS, K>::NB * 32 <= 288) ? 2 : 1)
+template <int WS, int K, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * Geo<WS, K>::NB * 32, MINB)
 window_attention_mma_kernel(const WinMmaParams p) {
   using G = Geo<WS, K>;
   constexpr int P = G::P, Tw = G::Tw, NB = G::NB, NT = G::NT, PS = G::PS, NR = G::NR, NRW = G::NRW;
@@ -178,20 +181,30 @@ window_attention_mma_kernel(const WinMmaParams p) {
         mma3(ck[nt], kh, kl, Rq[rq_row[nt] + ks * 8 + t], Rq[rq_row[nt] + ks * 8 + t + 4]);
       }
     }
-    // scatter: C element (row, n) -> pixel of the window, if it exists
+    // scatter: C element (row, n) -> pixel of the window, if it exists.  n = 8 nt + 2t + (c & 1) -> (a, b) = (n / NBX, n % NBX),
+    // advanced incrementally over nt
+    int a_[2], b_[2];
 #pragma unroll
-    for (int nt = 0; nt < NSUBT; ++nt)
+    for (int e = 0; e < 2; ++e) { a_[e] = (2 * t + e) / NBX; b_[e] = (2 * t + e) % NBX; }
+    const int ry_[2] = {(g / K) / BW, ((g + 8) / K) / BW}, rx_[2] = {(g / K) % BW, ((g + 8) / K) % BW};
+#pragma unroll
+    for (int nt = 0; nt < NSUBT; ++nt) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int row = g + 8 * (c >> 1), n = nt * 8 + 2 * t + (c & 1);
-        const int a = n / NBX, b = n % NBX, rp = row / K, ry = rp / BW, rx = rp % BW;
-        if (n < NSUB) {
+        const int row = g + 8 * (c >> 1), a = a_[c & 1], b = b_[c & 1], ry = ry_[c >> 1], rx = rx_[c >> 1];
+        if (a < G::NA) {
           const int yp = ry + WS - 1 - a, xp = rx + WS - 1 - b;                  // QR[i][pp]
-          if (yp >= 0 && yp < WS && xp >= 0 && xp < WS) myqr[row * PS + yp * WS + xp] = cq[nt][c];
+          if ((unsigned)yp < (unsigned)WS && (unsigned)xp < (unsigned)WS) myqr[row * PS + yp * WS + xp] = cq[nt][c];
           const int yi = a - BH + 1 + ry, xi = b - BW + 1 + rx;                  // KR[j][pi]
-          if (yi >= 0 && yi < WS && xi >= 0 && xi < WS) KRs[(slot0 + row) * PS + yi * WS + xi] = ck[nt][c];
+          if ((unsigned)yi < (unsigned)WS && (unsigned)xi < (unsigned)WS) KRs[(slot0 + row) * PS + yi * WS + xi] = ck[nt][c];
         }
       }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {          // n += 8
+        b_[e] += 8 % NBX; a_[e] += 8 / NBX;
+        if (b_[e] >= NBX) { b_[e] -= NBX; ++a_[e]; }
+      }
+    }
   }
   __syncthreads();                         // KR of every block is complete; Rk / Rq are dead
   for (int i = tid; i < WPC * Tw * 8; i += NTHREADS) {                  // V rows into the table's space, asynchronously
@@ -328,7 +341,7 @@ window_attention_mma_kernel(const WinMmaParams p) {
   }
 }
 
-template <int WS, int K, int WPC>
+template <int WS, int K, int WPC, int MINB>
 int launch_mma(const WinMmaParams& p, cudaStream_t stream) {
   using G = Geo<WS, K>;
   constexpr int NWARP = WPC * G::NB;
@@ -337,11 +350,11 @@ int launch_mma(const WinMmaParams& p, cudaStream_t stream) {
                                            (TAB > VSZ ? TAB : VSZ)) + sizeof(int) * (WPC * G::Tw + WPC * G::P);
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(window_attention_mma_kernel<WS, K, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(window_attention_mma_kernel<WS, K, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   dim3 grid((p.nwin + WPC - 1) / WPC, kHeads);
-  window_attention_mma_kernel<WS, K, WPC><<<grid, NWARP * 32, smem, stream>>>(p);
+  window_attention_mma_kernel<WS, K, WPC, MINB><<<grid, NWARP * 32, smem, stream>>>(p);
   count_launch();
   return check_launch("window_attention_mma");
 }
@@ -356,8 +369,10 @@ int window_attention_mma(const float* qkv, const float* table, int B, int Hp, in
   p.qkv = qkv; p.table = table; p.out = out;
   p.B = B; p.Hp = Hp; p.Wp = Wp; p.shift = shift; p.self_edge = self_edge;
   p.nwy = Hp / ws; p.nwx = Wp / ws; p.nwin = B * p.nwy * p.nwx;
-  if (ws == 6 && K == 4) return launch_mma<6, 4, 1>(p, stream);
-  if (ws == 4 && K == 1) return launch_mma<4, 1, 8>(p, stream);
+  static int minb = 0;
+  if (!minb) { const char* e = getenv("NMRF_B200_WIN_MINB"); minb = e ? atoi(e) : 2; }
+  if (ws == 6 && K == 4) return minb == 1 ? launch_mma<6, 4, 1, 1>(p, stream) : launch_mma<6, 4, 1, 2>(p, stream);
+  if (ws == 4 && K == 1) return minb == 1 ? launch_mma<4, 1, 8, 1>(p, stream) : launch_mma<4, 1, 8, 2>(p, stream);
   set_error("window_attention_mma: unsupported geometry ws=%d K=%d", ws, K);
   return NMRF_ERR_BAD_ARG;
 }

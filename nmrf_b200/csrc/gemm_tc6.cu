@@ -218,7 +218,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
           for (int j = 0; j < 4; ++j) {
             const float h = rna_tf32_fast(vv[j]);
             hi[cc * 4 + j] = __float_as_uint(h);
-            lo[cc * 4 + j] = __float_as_uint(rna_tf32_fast(vv[j] - h));
+            lo[cc * 4 + j] = __float_as_uint(vv[j] - h);     // unrounded: the tensor core truncates, losing <= 2^-25 |x|
           }
         }
         trace(tp2, 1024 + unit * 8 + 1);

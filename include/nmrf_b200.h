@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NMRF_B200_ABI_VERSION 3
+#define NMRF_B200_ABI_VERSION 4
 
 enum {
   NMRF_OK = 0,
@@ -194,6 +194,23 @@ int nmrf_ms_deform_attn_forward_dev(const float* value, const int64_t* spatial_s
                                     const float* sampling_loc, const float* attn_weight,
                                     int N, int S, int M, int Dh, int L, int Lq, int P,
                                     float* out, void* stream);
+
+/* ---- N2 (next row of the scope table): element-wise glue of the convolutional feature extractor, NHWC ----
+ * replaces nn.InstanceNorm2d + ReLU + residual add between the convolutions of the reference's Backbone /
+ * conv heads (nmrf/models/backbone.py:13-45, NMRF.py:56-65, DPN.py:45-49) and prepares the next convolution's
+ * error-compensated operand.  All tensors NHWC ([N, H*W, C], C % 4 == 0).
+ *   stats [N, C, 2] doubles, ZEROED by the caller: sum and sum of squares over H*W (biased variance, eps 1e-5).
+ *   apply:  y = IN(x) if x_stats else x;  relu if relu_inner;  y += (IN(r) if r_stats else r) if r;  relu if relu_outer;
+ *           out_plain [N,HW,C] (or NULL) = y;  out_cat3 [N,HW,3C] (or NULL) = [hi | lo | hi] with hi = rn_tf32(y),
+ *           lo = rn_tf32(y - hi): convolving it with weights [w_hi | w_hi | w_lo] (input-channel concatenation) is
+ *           x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, i.e. 3xTF32 in one library call.
+ */
+int nmrf_instnorm_stats(const float* x, int N, int HW, int C, double* stats, void* stream);
+int nmrf_instnorm_apply(const float* x, const double* x_stats, const float* r, const double* r_stats,
+                        int N, int HW, int C, int relu_inner, int relu_outer,
+                        float* out_plain, float* out_cat3, void* stream);
+/* x [rows, C] -> out [rows, 3C] = [hi | lo | hi] */
+int nmrf_split_cat3(const float* x, int64_t rows, int C, float* out, void* stream);
 
 #ifdef __cplusplus
 }

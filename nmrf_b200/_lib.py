@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class GemmArgs(Structure):
@@ -40,6 +40,9 @@ _I, _F, _P = c_int, c_float, c_void_p
 SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
     "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
+    "nmrf_instnorm_stats": [_P, _I, _I, _I, _P, _P],
+    "nmrf_instnorm_apply": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
+    "nmrf_split_cat3": [_P, c_int64, _I, _P, _P],
     "nmrf_set_attention_impl": [_I],
     "nmrf_debug_set_trace": [_P],
     "nmrf_pack_weight_tiles": [_P, _I, _I, _P, _P, _P],

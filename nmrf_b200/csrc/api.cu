@@ -41,6 +41,9 @@ int window_attention(const float*, const float*, int, int, int, int, int, int, i
 int stripe_attention(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int stripe_attention_tc(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 bool window_attention_mma_supported(int K, int ws);
+int instnorm_stats(const float*, int, int, int, double*, cudaStream_t);
+int instnorm_apply(const float*, const double*, const float*, const double*, int, int, int, int, int, float*, float*, cudaStream_t);
+int split_cat3(const float*, long long, int, float*, cudaStream_t);
 int window_attention_mma(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int,
                     int, int, float, float*, float*, cudaStream_t);
@@ -155,6 +158,16 @@ int nmrf_window_attention(const float* qkv, const float* table, int B, int Hp, i
     return window_attention_mma(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask, out, ST(stream));
   }
   return window_attention(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask, out, ST(stream));
+}
+int nmrf_instnorm_stats(const float* x, int N, int HW, int C, double* stats, void* stream) {
+  return instnorm_stats(x, N, HW, C, stats, ST(stream));
+}
+int nmrf_instnorm_apply(const float* x, const double* x_stats, const float* r, const double* r_stats, int N, int HW, int C,
+                        int relu_inner, int relu_outer, float* out_plain, float* out_cat3, void* stream) {
+  return instnorm_apply(x, x_stats, r, r_stats, N, HW, C, relu_inner, relu_outer, out_plain, out_cat3, ST(stream));
+}
+int nmrf_split_cat3(const float* x, int64_t rows, int C, float* out, void* stream) {
+  return split_cat3(x, (long long)rows, C, out, ST(stream));
 }
 int nmrf_select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K, int Hp,
                        int Wp, int top, int left, float* disp_curr, void* stream) {

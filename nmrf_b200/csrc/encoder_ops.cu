@@ -1,0 +1,165 @@
+// N2 ("next"): element-wise glue of the convolutional feature extractor and the conv heads, NHWC.
+// The convolutions themselves stay library calls (cuDNN implicit GEMM on [x_hi | x_lo | x_hi] x [w_hi | w_hi | w_lo],
+// i.e. error-compensated 3xTF32 in ONE call); what is fused here is everything between two convolutions, which in torch
+// took 5 of the encoder's 7.8 ms (NCHW<->NHWC copies around InstanceNorm, batch_norm statistics / transform, ReLU,
+// residual add, the hi/lo split and the `y +=` accumulations of three separate convolutions):
+//   instnorm_stats : per (sample, channel) sum and sum of squares over H*W   (reference: nn.InstanceNorm2d, backbone.py:28-41)
+//   instnorm_apply : y = relu?(IN(x)) [+ r | + IN(r)] -> relu? -> plain fp32 and/or the [hi | lo | hi] operand of the next conv
+//   split_cat3     : plain tensor -> [hi | lo | hi]
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace nmrf {
+namespace {
+using tc::rna_tf32_fast;
+
+constexpr int ST_PIX = 64;     // pixels per thread in the statistics pass (fp32 partial sums stay short)
+
+// grid (chunks, N); block = (C/4) * ppb threads: thread -> (pixel lane, 4 channels)
+__global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C, double* __restrict__ stats) {
+  extern __shared__ double red[];                  // [ppb][C][2]
+  const int c4n = C >> 2, ppb = blockDim.x / c4n;
+  const int pl = threadIdx.x / c4n, c4 = threadIdx.x % c4n;
+  const int n = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * ppb * ST_PIX;
+  const float* base = x + ((size_t)n * HW) * C + c4 * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+  for (int k = 0; k < ST_PIX; ++k) {
+    const long long p = p0 + (long long)k * ppb + pl;
+    if (p < HW) {
+      const float4 v = *reinterpret_cast<const float4*>(base + (size_t)p * C);
+      s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+      q[0] = fmaf(v.x, v.x, q[0]); q[1] = fmaf(v.y, v.y, q[1]); q[2] = fmaf(v.z, v.z, q[2]); q[3] = fmaf(v.w, v.w, q[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[((size_t)pl * C + c4 * 4 + j) * 2 + 0] = (double)s[j];
+    red[((size_t)pl * C + c4 * 4 + j) * 2 + 1] = (double)q[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C * 2; i += blockDim.x) {
+    double a = 0.0;
+    for (int l = 0; l < ppb; ++l) a += red[(size_t)l * C * 2 + i];
+    atomicAdd(stats + (size_t)n * C * 2 + i, a);
+  }
+}
+
+__device__ __forceinline__ void mean_rstd(const double* st, int HW, float& mean, float& rstd) {
+  const double m = st[0] / HW;
+  double var = st[1] / HW - m * m;                 // biased variance, like InstanceNorm
+  if (var < 0.0) var = 0.0;
+  mean = (float)m;
+  rstd = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+struct ApplyArgs {
+  const float* x; const double* xs; const float* r; const double* rs;
+  float* plain; float* cat3;
+  int HW, C, relu_inner, relu_outer;
+  long long total4;                                 // N*HW*C/4
+};
+
+__global__ void instnorm_apply_kernel(const ApplyArgs a) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.total4) return;
+  const int c4n = a.C >> 2;
+  const int c = (int)(i % c4n) * 4;
+  const long long pix = i / c4n;                    // n*HW + p
+  const int n = (int)(pix / a.HW);
+  float4 v = *reinterpret_cast<const float4*>(a.x + pix * a.C + c);
+  float o[4] = {v.x, v.y, v.z, v.w};
+  if (a.xs) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float m, rs;
+      mean_rstd(a.xs + ((size_t)n * a.C + c + j) * 2, a.HW, m, rs);
+      o[j] = (o[j] - m) * rs;
+    }
+  }
+  if (a.relu_inner) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+  if (a.r) {
+    const float4 rv = *reinterpret_cast<const float4*>(a.r + pix * a.C + c);
+    float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+    if (a.rs) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float m, rs;
+        mean_rstd(a.rs + ((size_t)n * a.C + c + j) * 2, a.HW, m, rs);
+        rr[j] = (rr[j] - m) * rs;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] += rr[j];
+  }
+  if (a.relu_outer) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+  }
+  if (a.plain) *reinterpret_cast<float4*>(a.plain + pix * a.C + c) = make_float4(o[0], o[1], o[2], o[3]);
+  if (a.cat3) {
+    float h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { h[j] = rna_tf32_fast(o[j]); l[j] = rna_tf32_fast(o[j] - h[j]); }
+    float* d = a.cat3 + pix * 3 * a.C + c;
+    const float4 h4 = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(d) = h4;
+    *reinterpret_cast<float4*>(d + a.C) = make_float4(l[0], l[1], l[2], l[3]);
+    *reinterpret_cast<float4*>(d + 2 * a.C) = h4;
+  }
+}
+
+// generic (any C): one thread per element
+__global__ void split_cat3_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const long long r = i / C;
+  const int c = (int)(i % C);
+  const float v = x[i], h = rna_tf32_fast(v), l = rna_tf32_fast(v - h);
+  float* d = out + r * 3 * C + c;
+  d[0] = h; d[C] = l; d[2 * C] = h;
+}
+}  // namespace
+
+int instnorm_stats(const float* x, int N, int HW, int C, double* stats, cudaStream_t stream) {
+  NMRF_REQUIRE(x && stats && N > 0 && HW > 0, "instnorm_stats: bad arguments");
+  NMRF_REQUIRE(C % 4 == 0 && C >= 4 && C <= 1024, "instnorm_stats: C=%d must be a multiple of 4 (<= 1024)", C);
+  const int c4n = C / 4;
+  int ppb = 256 / c4n;
+  if (ppb < 1) ppb = 1;
+  const int threads = ppb * c4n;
+  const int chunks = (HW + ppb * ST_PIX - 1) / (ppb * ST_PIX);
+  const size_t smem = (size_t)ppb * C * 2 * sizeof(double);
+  NMRF_REQUIRE(smem <= 48 * 1024, "instnorm_stats: C=%d needs %zu B of shared memory", C, smem);
+  instnorm_stats_kernel<<<dim3(chunks, N), threads, smem, stream>>>(x, HW, C, stats);
+  count_launch();
+  return check_launch("instnorm_stats");
+}
+
+int instnorm_apply(const float* x, const double* x_stats, const float* r, const double* r_stats, int N, int HW, int C,
+                   int relu_inner, int relu_outer, float* out_plain, float* out_cat3, cudaStream_t stream) {
+  NMRF_REQUIRE(x && N > 0 && HW > 0 && (out_plain || out_cat3), "instnorm_apply: bad arguments");
+  NMRF_REQUIRE(C % 4 == 0, "instnorm_apply: C=%d must be a multiple of 4", C);
+  NMRF_REQUIRE(r || !r_stats, "instnorm_apply: r_stats without r");
+  ApplyArgs a;
+  a.x = x; a.xs = x_stats; a.r = r; a.rs = r_stats; a.plain = out_plain; a.cat3 = out_cat3;
+  a.HW = HW; a.C = C; a.relu_inner = relu_inner; a.relu_outer = relu_outer;
+  a.total4 = (long long)N * HW * (C / 4);
+  instnorm_apply_kernel<<<(unsigned)((a.total4 + 255) / 256), 256, 0, stream>>>(a);
+  count_launch();
+  return check_launch("instnorm_apply");
+}
+
+int split_cat3(const float* x, long long rows, int C, float* out, cudaStream_t stream) {
+  NMRF_REQUIRE(x && out && rows > 0 && C > 0, "split_cat3: bad arguments");
+  const long long n = rows * C;
+  split_cat3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, rows, C, out);
+  count_launch();
+  return check_launch("split_cat3");
+}
+
+}  // namespace nmrf

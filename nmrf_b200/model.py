@@ -13,6 +13,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .exactconv import ExactConvCache, patch_convs
+from .encoder import FusedEncoder
+from .backbone import Backbone
 from .hotpath import HotPathConfig, HotPathPlan, PackedWeights
 
 
@@ -211,6 +213,10 @@ class NMRF(nn.Module):
         # "fp32" = cuDNN with TF32 disabled (slow on B200), "tf32" = cuDNN default (fast, breaks parity)
         self.conv_mode = "3xtf32"
         self._conv_cache = ExactConvCache()
+        # fused NHWC execution of the stock ResNet-style backbone + conv heads (encoder.py); other backbones fall back to
+        # running their torch modules with the 3xTF32 convolution wrapper
+        self.fused_encoder = True
+        self._encoder = None
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ---- plumbing ---------------------------------------------------------------------------
@@ -222,6 +228,7 @@ class NMRF(nn.Module):
         """Drop packed weights and launch plans (call after changing parameters in place)."""
         self._packed = None
         self._plans = {}
+        self._encoder = None
         if hasattr(self, "_conv_cache"):
             self._conv_cache.clear()
 
@@ -271,6 +278,15 @@ class NMRF(nn.Module):
             img2 = F.pad(img2, [0, pad_w, 0, pad_h], mode="replicate")
         img1 = img1.contiguous(memory_format=torch.channels_last)
         img2 = img2.contiguous(memory_format=torch.channels_last)
+        if self.fused_encoder and self.compat and self.conv_mode == "3xtf32" and type(self.backbone) is Backbone:
+            Hp_, Wp_ = img1.shape[-2:]
+            h8, w8 = Hp_ // 8, Wp_ // 8
+            plan = self.plan_for(B, self.backbone.output_dim, h8, w8, H, W)
+            if self._encoder is None:
+                self._encoder = FusedEncoder(self)
+            self._encoder.run(img1, img2, plan)
+            plan.run()
+            return self._outputs(plan, B)
         # exact-fp32 convolutions: cuDNN's default TF32 moves the features by ~5e-4 relative, which flips
         # top-K / argmax decisions downstream (EPE 0.2-0.4 px measured) -- same reason as DESIGN.md §3
         self._conv_cache.enabled = self.conv_mode == "3xtf32"
@@ -292,6 +308,9 @@ class NMRF(nn.Module):
                 cc[0].copy_(c[:B]); cc[1].copy_(c[B:])
                 gw[0].copy_(g[:B]); gw[1].copy_(g[B:])
         plan.run()
+        return self._outputs(plan, B)
+
+    def _outputs(self, plan, B):
         K = self.num_proposals
         return {
             "proposal": plan.labels.reshape(B, -1, K).clone(),

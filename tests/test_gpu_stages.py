@@ -343,3 +343,53 @@ def test_msda_error_behaviour():
     with pytest.raises(RuntimeError, match="im2col_step"):
         msda.ms_deform_attn_forward(v, shp, st, loc, w, 2)
     assert msda.ms_deform_attn_forward(v, shp, st, loc, w, 3).shape == (3, 5, 8)
+
+
+# ---- N2: feature-extractor glue (instance norm statistics / fused apply) and the fused encoder ----
+@pytest.mark.parametrize("N,H,W,C", [(2, 17, 23, 64), (1, 40, 31, 96), (2, 9, 12, 128), (1, 6, 7, 384)])
+def test_instnorm_kernels(ops, N, H, W, C):
+    import torch.nn.functional as F
+    from nmrf_b200 import _lib
+    g = torch.Generator().manual_seed(C + H)
+    x = (torch.randn(N, H, W, C, generator=g) * 3 + 1.5).cuda()
+    r = torch.randn(N, H, W, C, generator=g).cuda()
+    st = lambda: torch.zeros(N, C, 2, dtype=torch.float64, device="cuda")
+    sx, sr = st(), st()
+    s = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib.nmrf_instnorm_stats(x.data_ptr(), N, H * W, C, sx.data_ptr(), s), "stats")
+    _lib.check(_lib.lib.nmrf_instnorm_stats(r.data_ptr(), N, H * W, C, sr.data_ptr(), s), "stats")
+    plain, cat3 = torch.empty_like(x), torch.empty(N, H, W, 3 * C, device="cuda")
+    _lib.check(_lib.lib.nmrf_instnorm_apply(x.data_ptr(), sx.data_ptr(), r.data_ptr(), sr.data_ptr(), N, H * W, C, 1, 1,
+                                            plain.data_ptr(), cat3.data_ptr(), s), "apply")
+    nchw = lambda t: t.permute(0, 3, 1, 2).double()
+    ref = F.relu(F.relu(F.instance_norm(nchw(x))) + F.instance_norm(nchw(r))).permute(0, 2, 3, 1)
+    assert rel_err(plain, ref) <= 2e-6
+    hi, lo = cat3[..., :C], cat3[..., C:2 * C]
+    assert torch.equal(cat3[..., 2 * C:], hi)
+    assert torch.equal((hi.view(torch.int32) & 0x1FFF), torch.zeros_like(hi, dtype=torch.int32))    # tf32-representable
+    assert rel_err(hi.double() + lo.double(), plain) <= 1e-6
+    # plain residual, no norm on it, inner relu only
+    _lib.check(_lib.lib.nmrf_instnorm_apply(x.data_ptr(), sx.data_ptr(), r.data_ptr(), None, N, H * W, C, 1, 0,
+                                            plain.data_ptr(), None, s), "apply")
+    ref = (F.relu(F.instance_norm(nchw(x))) + nchw(r)).permute(0, 2, 3, 1)
+    assert rel_err(plain, ref) <= 2e-6
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 40, 72)])
+def test_fused_encoder_matches_module_path(B, H, W):
+    """encoder.FusedEncoder (NHWC, fused glue, one cuDNN call per conv) against the torch modules run with the
+    3xTF32 convolution wrapper: the hot path's inputs must agree to fp32 rounding"""
+    from helpers import build_product_model
+    from nmrf_b200.synthetic import synthetic_pair
+    model, _ = build_product_model(64, 2, (1, 1, 1), 0, "reference")
+    model = model.cuda()
+    img1, img2 = (t.cuda() for t in synthetic_pair(B, H, W, 64, index=1))
+    names = ("f1_8", "f2_8", "context")
+    outs = {}
+    for fused in (True, False):
+        model.fused_encoder = fused
+        model.forward_device(img1, img2)
+        plan = model.plan_for(B, 256, H // 8, W // 8, H, W)
+        outs[fused] = [getattr(plan, n).clone() for n in names] + [t.clone() for t in plan.cc8 + plan.gw8 + plan.cc4 + plan.gw4]
+    for a, b in zip(outs[True], outs[False]):
+        assert rel_err(a, b) <= 2e-5

@@ -38,7 +38,7 @@ def test_binding_matches_header():
 
 def test_helpers_work_without_a_gpu():
     from nmrf_b200 import _lib
-    assert _lib.lib.nmrf_abi_version() == _lib.ABI_VERSION == 3
+    assert _lib.lib.nmrf_abi_version() == _lib.ABI_VERSION == 4
     assert isinstance(_lib.launch_count(), int)
     # argument validation happens before any CUDA call: a bad GEMM is rejected with a message
     a = _lib.GemmArgs()

@@ -181,7 +181,7 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
@@ -232,7 +232,7 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {

@@ -201,7 +201,7 @@ token_gemm_tc_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, int
       const int buf = unit % TC_NB;
       if (nc == 0) abuf = (akb++) & 1;
       asm volatile("bar.sync %0, %1;" ::"r"(1 + buf), "r"(TC_BLOCK) : "memory");      // unit's operands are in shared memory
-      if (lane == 0) {
+      if (elect_one()) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int n0 = nc * TC_BN;
         const int bn = min(TC_BN, a.N - n0);

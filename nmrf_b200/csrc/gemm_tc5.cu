@@ -225,7 +225,7 @@ token_gemm_tc5_kernel(const nmrf_gemm_args a, const float* __restrict__ W_lo, in
         trace(tp, 2048 + unit * 4 + 0);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G5_HANDOFF) : "memory");
         trace(tp, 2048 + unit * 4 + 1);
-        if (lane == 0) {
+        if (elect_one()) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const int bn = min(G5_BN, tc_.npass - nc * G5_BN);
           const uint32_t idesc = make_idesc(bn);

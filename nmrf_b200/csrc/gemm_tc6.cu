@@ -259,9 +259,10 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
         const int slot = unit % G6_NB;
         trace(tp, 2048 + unit * 4 + 0);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");      // A of this unit is in TMEM
+        trace(tp, 2048 + unit * 4 + 3);
         mbar_wait_warp(&sm.full_b[slot], (unit / G6_NB) & 1);                             // B tiles have landed
         trace(tp, 2048 + unit * 4 + 1);
-        if (lane == 0) {
+        if (elect_one()) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t dBh = make_desc(smem_u32(sB_hi(slot))), dBl = make_desc(smem_u32(sB_lo(slot)));
           const uint32_t d = tmem + (uint32_t)(as * G6_BN);
@@ -282,7 +283,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
     }
   } else if (warp == G6_TMA_WARP) {
     // =============================================== weight tiles (TMA) ===============================================
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t unit = 0;
       for (int t = blockIdx.x; t < ntiles; t += tstep) {
         const int nchunk = t / n_rb;

@@ -9,6 +9,22 @@ constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a CONVERGED warp (elect.sync).  tcgen05.mma / tcgen05.commit / cp.async.bulk are uniform-datapath
+// instructions: under `if (lane == 0)` ptxas cannot prove a single active lane and wraps each of them in an
+// ELECT ... BRA.U.ANY loop, which caps the issue rate at ~93 cycles per MMA (tools/probes/umma_probe.cu: a 128x128x8
+// tf32 MMA then takes 93 cycles instead of its 64-cycle floor, a 128x32x8 one 93 instead of 16).  With the elect.sync
+// predicate the instructions are emitted back to back and run at the hardware floor.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+
 __device__ __forceinline__ float rna_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));

@@ -41,8 +41,10 @@ for name, rows, Kx, Ke, N, ln, act, res in [("fc2", 34560, 512, 0, 128, False, 0
     for u, r in enumerate(p2[:12]):
         nxt = (p2[u + 1][0] - r[5]) if u + 1 < len(p2) else None
         print("   u%02d" % u, r[0], "|", r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], "|", nxt)
-    print("  mma (before sync, wait, issue):")
-    for u, r in enumerate(mma[:24]):
-        print("   u%02d" % u, r[0], r[1] - r[0], r[2] - r[1])
+    print("  mma (before sync | bar.sync, full_b wait, issue | gap to next):")
+    m4 = [[(t[2048 + u * 4 + k] - t0) for k in range(4)] for u in range(40) if t[2048 + u * 4]]
+    for u, r in enumerate(m4[:28]):
+        nxt = (m4[u + 1][0] - r[2]) if u + 1 < len(m4) else None
+        print("   u%02d" % u, r[0], "|", r[3] - r[0], r[1] - r[3], r[2] - r[1], "|", nxt)
     print("  epilogue (start, wait, drain):", [(r[0], r[1] - r[0], r[2] - r[1]) for r in epi])
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "gemm_trace.json"), "w"))

@@ -9,10 +9,18 @@
 namespace nmrf { void set_error(const char*, ...) {} int check_launch(const char*) { return 0; } void count_launch(int) {} }
 using namespace nmrf::tc;
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}"
+               : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFF));
+  return pred != 0;
+}
 __device__ __forceinline__ uint32_t idesc_n(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
 
 // mode: 0 = TS (A in TMEM), 1 = SS.  noise: 0 none, 1 = warps 1..3 do LDS.128 loops, 2 = STS.128 loops, 3 = 12 extra warps LDS
-__global__ void __launch_bounds__(512, 1) probe(int mode, int n, int iters, int noise, long long* out) {
+template <int ELECT, int MODE>
+__global__ void __launch_bounds__(512, 1) probe(int n, int iters, int noise, long long* out) {
+  constexpr int mode = MODE;
   extern __shared__ __align__(1024) uint8_t dsm[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base;
@@ -32,7 +40,7 @@ __global__ void __launch_bounds__(512, 1) probe(int mode, int n, int iters, int 
   __shared__ volatile int stop;
   if (tid == 0) stop = 0;
   __syncthreads();
-  if (tid == 0) {
+  if (warp == 0 && (ELECT ? elect_one() : tid == 0)) {
     const uint32_t idesc = idesc_n(n);
     // B tiles: 3 slots x (hi, lo) of [256 rows x 32 k] = 32 KB each at base + slot*64KB... keep to 5 x 32 KB
     const long long t0 = clock64();
@@ -61,6 +69,7 @@ __global__ void __launch_bounds__(512, 1) probe(int mode, int n, int iters, int 
     const long long t2 = clock64();
     stop = 1;
     if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (warp == 0) {
   } else if (noise && warp >= 1 && (noise == 3 ? warp < 13 : warp < 4)) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     float4* p = reinterpret_cast<float4*>(base + 131072 + 32768) + tid;     // scratch region not used as an operand: 24 KB
@@ -84,17 +93,24 @@ int main() {
   long long* out;
   cudaMalloc(&out, 64);
   const int dyn = 200 * 1024;
-  cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  cudaFuncSetAttribute(probe<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  cudaFuncSetAttribute(probe<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  cudaFuncSetAttribute(probe<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
+  cudaFuncSetAttribute(probe<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn);
   const int iters = 200;
-  for (int noise = 0; noise < 4; ++noise)
+  for (int elect = 0; elect < 2; ++elect)
+  for (int noise = 0; noise < 4; noise += 3)
     for (int mode = 0; mode < 2; ++mode)
       for (int n : {64, 128, 256}) {
         if (n == 256 && mode == 0 && false) continue;
-        probe<<<148, 512, dyn>>>(mode, n, iters, noise, out);
+        if (elect == 0 && mode == 0) probe<0, 0><<<148, 512, dyn>>>(n, iters, noise, out);
+        if (elect == 0 && mode == 1) probe<0, 1><<<148, 512, dyn>>>(n, iters, noise, out);
+        if (elect == 1 && mode == 0) probe<1, 0><<<148, 512, dyn>>>(n, iters, noise, out);
+        if (elect == 1 && mode == 1) probe<1, 1><<<148, 512, dyn>>>(n, iters, noise, out);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[2] = {0, 0};
         cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
-        printf("noise %d %s N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %d)%s\n", noise, mode ? "SS" : "TS", n,
+        printf("elect %d noise %d %s N=%3d: issue %.1f cyc/MMA, complete %.1f cyc/MMA (floor %d)%s\n", elect, noise, mode ? "SS" : "TS", n,
                (double)h[0] / (iters * 12), (double)h[1] / (iters * 12), n / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
         if (e != cudaSuccess) return 1;
       }

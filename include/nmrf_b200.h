@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NMRF_B200_ABI_VERSION 4
+#define NMRF_B200_ABI_VERSION 5
 
 enum {
   NMRF_OK = 0,
@@ -75,6 +75,30 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
 /* w [N,K] row-major (device) -> hi/lo tile images, K zero-padded to a multiple of 32, N to a multiple of 128:
  * hi_tiles / lo_tiles must hold ceil(N/128)*ceil(K/32)*4096 floats each. */
 int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float* lo_tiles, void* stream);
+/* ---- fused block tail: proj + residual + LayerNorm + Mlp in ONE launch ----------------------------
+ *   x1 = concat(X[r, 0:Kx], E[r, 0:Ke]) . W1cat^T + bias_mid        (SwinNMP / CSWinNMP: x + proj(attn), NMP.py:358-359,
+ *                                                                    570-571; the caller puts [Wproj | I] in the stream and the
+ *                                                                    residual stream x in E, so the add happens in the tensor core)
+ *   Y  = x1 + fc2( GELU( fc1( LN(x1) ) ) ) + b_fc2                   (x + Mlp(norm2(x)), NMP.py:362-363,572-573; timm Mlp 128->512->128)
+ * Wstream: (Kx+Ke)/32 + 32 units of 8192 floats (16 KB hi image + 16 KB lo image, SWIZZLE_128B shared-memory images of
+ * [128 x 32] fp32 tiles):  P1(0..n1-1), then F1(c,p) at n1 + 2c + p, then F2(c,q) at n1 + 16 + 2c + q (c = hidden chunk of 64,
+ * 0..7; every CTA walks the k-blocks and the chunks starting from its own rotation, so the fp32 summation order differs per
+ * tile):  P1(j)[n,k] = W1cat[n, 32j+k];  F1(c,p)[r,k] = Wfc1[64c + r%64, 32(2p + r/64) + k];  F2(c,q)[n,k] = Wfc2[n, 64c+32q+k]
+ * (nmrf_b200/hotpath.py: pack_mlp_stream).  bias_out = bias_mid + b_fc2.  Kx+Ke must be a multiple of 32 (<= 512);
+ * Y may alias E (each tile is read completely before it is written).  Same 3xTF32 arithmetic as nmrf_token_gemm. */
+typedef struct {
+  const float* X; int ldx; int Kx;
+  const float* E; int lde; int Ke;             /* may be NULL (Ke = 0) */
+  const float* Wstream;
+  const float* bias_mid;                       /* [128] */
+  const float* ln_gamma; const float* ln_beta; /* [128] */
+  const float* b1;                             /* [512] fc1 bias */
+  const float* bias_out;                       /* [128] */
+  float* Y; int ldy;
+  int rows;
+} nmrf_mlp_args;
+int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream);
+
 /* debug tooling: device buffer of 4096 int64 that CTA 0 of the tensor-core GEMM fills with clock64() stamps (NULL = off) */
 int nmrf_debug_set_trace(void* dev_i64_4096);
 /* hi = rna_tf32(w), lo = rna_tf32(w - hi), elementwise over n floats (device pointers) */

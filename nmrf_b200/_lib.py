@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class GemmArgs(Structure):
@@ -29,6 +29,21 @@ class GemmArgs(Structure):
     ]
 
 
+class MlpArgs(Structure):
+    """mirror of nmrf_mlp_args"""
+    _fields_ = [
+        ("X", c_void_p), ("ldx", c_int), ("Kx", c_int),
+        ("E", c_void_p), ("lde", c_int), ("Ke", c_int),
+        ("Wstream", c_void_p),
+        ("bias_mid", c_void_p),
+        ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
+        ("b1", c_void_p),
+        ("bias_out", c_void_p),
+        ("Y", c_void_p), ("ldy", c_int),
+        ("rows", c_int),
+    ]
+
+
 class SeedWeights(Structure):
     """mirror of nmrf_seed_weights"""
     _fields_ = [("w0", c_void_p), ("b0", c_void_p), ("w1", c_void_p), ("b1", c_void_p),
@@ -39,6 +54,7 @@ class SeedWeights(Structure):
 _I, _F, _P = c_int, c_float, c_void_p
 SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
+    "nmrf_mlp_chain": [POINTER(MlpArgs), _P],
     "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
     "nmrf_instnorm_stats": [_P, _I, _I, _I, _P, _P],
     "nmrf_instnorm_apply": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],

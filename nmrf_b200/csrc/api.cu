@@ -30,6 +30,8 @@ int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stre
 int gemm_set_trace(long long* dev_ptr);
 int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
+int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
+int mlp_set_trace(long long* dev_ptr);
 int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
@@ -57,6 +59,7 @@ int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const f
 
 using namespace nmrf;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
+static_assert(sizeof(nmrf_gemm_args) == 144 && sizeof(nmrf_mlp_args) == 96, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
 
 // NMRF_B200_ATTN=simt selects the fp32-FMA attention kernels (default: tcgen05 3xTF32)
 static std::atomic<int> g_attn_tc{-1};
@@ -100,6 +103,17 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
   }
   return token_gemm_simt(*a, ST(stream));
 }
+int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream) {
+  NMRF_REQUIRE(a && a->X && a->Wstream && a->Y && a->bias_mid && a->bias_out && a->ln_gamma && a->ln_beta && a->b1,
+               "mlp_chain: null pointer");
+  NMRF_REQUIRE(a->rows >= 0, "mlp_chain: rows=%d", a->rows);
+  NMRF_REQUIRE(a->Kx > 0 && a->Kx % 32 == 0 && a->Ke >= 0 && a->Ke % 32 == 0 && a->Kx + a->Ke <= 512,
+               "mlp_chain: Kx=%d Ke=%d must be multiples of 32, sum <= 512", a->Kx, a->Ke);
+  NMRF_REQUIRE((a->Ke == 0) == (a->E == nullptr), "mlp_chain: E/Ke mismatch");
+  NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldy % 4 == 0 && (a->Ke == 0 || a->lde % 4 == 0), "mlp_chain: bad leading dimension");
+  if (a->rows == 0) return NMRF_OK;
+  return mlp_chain(*a, ST(stream));
+}
 int nmrf_set_attention_impl(int tensor_cores) {
   g_attn_tc.store(tensor_cores ? 1 : 0, std::memory_order_relaxed);
   return NMRF_OK;
@@ -109,6 +123,7 @@ int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float*
 }
 int nmrf_debug_set_trace(void* dev_i64_4096) {
   gemm_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
+  mlp_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
   return gemm6_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
 }
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {

@@ -57,22 +57,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try(addr, parity)) return;
   __trap();
 }
-// Whole-warp wait (every lane must call it, converged): ONE lane polls, the rest park at the warp barrier.  32 lanes x many
-// warps spinning on try_wait flood the MIO queue the producers' LDS / LDGSTS / STTM go through (a third of all issued
-// instructions of the first warp-specialised GEMM were this spin).  `sleep_ns` > 0 backs off between polls: for waits
-// with slack (an epilogue waiting for a whole tile of MMAs).
+// Whole-warp wait (every lane must call it, converged): ALL lanes poll.  An earlier version let one lane poll and parked the
+// other 31 at __syncwarp to keep the spin out of the MIO queue; measured inside the GEMM kernels (tools/mlp_trace.py), the
+// reconvergence of that lane-divergent wait and the elect.sync / warp-collective instruction after it cost 600-750 cycles
+// EACH per use (10 cycles in isolation), i.e. ~1400 cycles per weight unit on the MMA warp's critical path.  A uniform
+// poll keeps the warp converged; try_wait suspends in hardware between polls, so the instruction rate stays moderate.
+// `sleep_ns` > 0 backs off between polls: for waits with slack (an epilogue waiting for a whole tile of MMAs).
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, uint32_t sleep_ns = 0) {
-  if ((threadIdx.x & 31) == 0) {
-    const uint32_t addr = smem_u32(bar);
-    bool ok = false;
+  const uint32_t addr = smem_u32(bar);
+  bool ok = false;
 #pragma unroll 1
-    for (uint32_t spin = 0; spin < SPIN_LIMIT && !ok; ++spin) {
-      ok = mbar_try(addr, parity);
-      if (!ok && sleep_ns) __nanosleep(sleep_ns);
-    }
-    if (!ok) __trap();
+  for (uint32_t spin = 0; spin < SPIN_LIMIT && !ok; ++spin) {
+    ok = mbar_try(addr, parity);
+    if (!ok && sleep_ns) __nanosleep(sleep_ns);
   }
-  __syncwarp();
+  if (!ok) __trap();
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100):

@@ -14,7 +14,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, SeedWeights, lib
+from ._lib import GemmArgs, MlpArgs, SeedWeights, lib
 
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
@@ -37,6 +37,11 @@ class HotPathConfig:
     num_refine_layers: int = 5
     eps: float = 1e-3                      # DPN.py:51
     tensor_cores: bool = True              # tcgen05 3xTF32 GEMMs (False / NMRF_B200_GEMM=simt: exact-fp32 FMA kernel)
+
+
+def _use_mlp_chain_default():
+    import os
+    return os.environ.get("NMRF_B200_MLP", "1") != "0"
 
 
 def _f32(t):
@@ -132,7 +137,9 @@ class _Launches:
         self.cost = []          # algorithmic (flops, HBM bytes) per launch, for the roofline report
         self._keep = []
         self._splits = {}
+        self._streams = {}
         self.tensor_cores = False
+        self.mlp_chain = False
 
     def add(self, fn, what, *args, flops=0.0, bytes=0.0):
         self.calls.append((fn, what, args))
@@ -181,6 +188,26 @@ class _Launches:
         flops = 2.0 * rows * N * (a.Kx + Ke)
         nbytes = 4.0 * (rows * a.Kx + (rows // max(ediv, 1)) * Ke + rows * N * (2 if R is not None else 1))
         self.add(lib.nmrf_token_gemm, what, ctypes.byref(a), flops=flops, bytes=nbytes)
+
+    def block_tail(self, what, att, x, rows, proj_w, proj_b, n2, fc1_w, fc1_b, fc2_w, fc2_b):
+        """x = x1 + Mlp(LN2(x1)), x1 = x + proj(att): ONE launch of nmrf_mlp_chain (SwinNMP / CSWinNMP tail, NMP.py:358-363,
+        570-573).  The residual stream rides the tensor core as an identity block appended to the proj weight."""
+        from . import ops
+        key = (proj_w.data_ptr(), fc1_w.data_ptr(), fc2_w.data_ptr())
+        if key not in self._streams:
+            eye = torch.eye(128, device=proj_w.device, dtype=torch.float32)
+            ws = ops.pack_mlp_stream(torch.cat([proj_w, eye], 1).contiguous(), fc1_w.contiguous(), fc2_w.contiguous())
+            self._streams[key] = (ws, (proj_b + fc2_b).contiguous())
+        ws, bias_out = self._streams[key]
+        a = MlpArgs()
+        a.X, a.ldx, a.Kx = att.data_ptr(), att.stride(0), 128
+        a.E, a.lde, a.Ke = x.data_ptr(), x.stride(0), 128
+        a.Wstream, a.bias_mid, a.ln_gamma, a.ln_beta = ws.data_ptr(), proj_b.data_ptr(), n2[0].data_ptr(), n2[1].data_ptr()
+        a.b1, a.bias_out = fc1_b.data_ptr(), bias_out.data_ptr()
+        a.Y, a.ldy, a.rows = x.data_ptr(), x.stride(0), rows
+        self.keep(a, att, x, ws, bias_out, proj_b, n2, fc1_b)
+        flops = 2.0 * rows * (128 * 128 + 2 * 128 * 512)
+        self.add(lib.nmrf_mlp_chain, what, ctypes.byref(a), flops=flops, bytes=4.0 * rows * 128 * 3)
 
     def run(self, stream):
         for fn, what, args in self.calls:
@@ -251,12 +278,22 @@ class HotPathPlan:
         self.pw = pw
         self.launches = _Launches()
         self.launches.tensor_cores = bool(cfg.tensor_cores) and _use_tc_default()
+        self.launches.mlp_chain = self.launches.tensor_cores and _use_mlp_chain_default()
         self._build(pw)
 
     # -------------------------------------------------------------------------------------------
     def _mlp_block(self, L_, T, n2, fc1_w, fc1_b, fc2_w, fc2_b, tag):
         L_.gemm(tag + ".fc1", self.x, fc1_w, self.hid, T, 512, ln=n2, bias=fc1_b, act=ACT_GELU)
         L_.gemm(tag + ".fc2", self.hid, fc2_w, self.x, T, 128, bias=fc2_b, R=self.x)
+
+    def _block_tail(self, L_, T, w, tag):
+        """proj + residual, then the Mlp block (NMP.py:358-363 / 570-573): one fused launch, or three token GEMMs"""
+        if L_.mlp_chain:
+            L_.block_tail(tag + ".tail", self.att, self.x, T, w["proj_w"], w["proj_b"], w["n2"], w["fc1_w"], w["fc1_b"],
+                          w["fc2_w"], w["fc2_b"])
+        else:
+            L_.gemm(tag + ".proj", self.att, w["proj_w"], self.x, T, 128, bias=w["proj_b"], R=self.x)
+            self._mlp_block(L_, T, w["n2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], tag)
 
     def _build(self, pw):
         c, g, L_ = self.cfg, self.geom, self.launches
@@ -283,8 +320,7 @@ class HotPathPlan:
             L_.gemm(t + ".qkv", self.x, w["qkv_w"], self.qkv, T8, 384, E=ctx, Ke=64, ediv=K, ln=w["n1"], bias=w["qkv_b"])
             L_.add(lib.nmrf_stripe_attention, t + ".stripe", ptr(self.qkv), B, h8, w8, K, ptr(w["gv0"]), ptr(w["gv1"]),
                    ptr(self.att))
-            L_.gemm(t + ".proj", self.att, w["proj_w"], self.x, T8, 128, bias=w["proj_b"], R=self.x)
-            self._mlp_block(L_, T8, w["n2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], t)
+            self._block_tail(L_, T8, w, t)
         # A7 ----------------------------------------------------------------------------------------
         (w0, b0), (w1, b1), (w2, b2) = pw.prop_head
         L_.gemm("prop_head.0", self.x, w0, self.h1, T8, 128, ln=pw.prop_norm, bias=b0, act=ACT_RELU)
@@ -340,8 +376,7 @@ class HotPathPlan:
             L_.gemm(t + ".qkv", self.x, wt["qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["n1"], bias=wt["qkv_b"])
             L_.add(lib.nmrf_window_attention, t + ".window", ptr(self.qkv), ptr(wt["table"]), B, Hp, Wp, K, ws, shift,
                    1 if with_self else 0, ptr(self.att))
-            L_.gemm(t + ".proj", self.att, wt["proj_w"], self.x, Tp, 128, bias=wt["proj_b"], R=self.x)
-            self._mlp_block(L_, Tp, wt["n2"], wt["fc1_w"], wt["fc1_b"], wt["fc2_w"], wt["fc2_b"], t)
+            self._block_tail(L_, Tp, wt, t)
 
     # -------------------------------------------------------------------------------------------
     def run(self):
@@ -362,14 +397,14 @@ class HotPathPlan:
                 taps.update(cost_volume=self.cost_volume.clone(), prob=self.prob.clone(), seeds=self.seeds.clone())
             elif what == "propagation.proj":
                 taps["prop_embed"] = self.x[:g["T8"]].reshape(-1, K, 128).clone()
-            elif what.startswith("prop") and what.endswith(".fc2") and what[4].isdigit():
-                taps[f"prop_layer{what[4:-4]}"] = self.x[:g["T8"]].reshape(-1, K, 128).clone()
+            elif what.startswith("prop") and what.endswith((".fc2", ".tail")) and what[4].isdigit():
+                taps[f"prop_layer{what[4:what.rindex('.')]}"] = self.x[:g["T8"]].reshape(-1, K, 128).clone()
             elif what == "prop_head.2":
                 taps["labels"] = self.labels.clone()
-            elif what.startswith("inference") and what.endswith(".fc2") and what[9].isdigit():
-                taps[f"inference_layer{what[9:-4]}"] = self.x[:g["T8p"]].reshape(-1, K, 128).clone()
-            elif what.startswith("refinement") and what.endswith(".fc2") and what[10].isdigit():
-                taps[f"refinement_layer{what[10:-4]}"] = self.x[:g["T4p"]].reshape(-1, 1, 128).clone()
+            elif what.startswith("inference") and what.endswith((".fc2", ".tail")) and what[9].isdigit():
+                taps[f"inference_layer{what[9:what.rindex('.')]}"] = self.x[:g["T8p"]].reshape(-1, K, 128).clone()
+            elif what.startswith("refinement") and what.endswith((".fc2", ".tail")) and what[10].isdigit():
+                taps[f"refinement_layer{what[10:what.rindex('.')]}"] = self.x[:g["T4p"]].reshape(-1, 1, 128).clone()
             elif what == "infer_score_head":
                 taps.update(delta=self.delta[:g["T8p"]].clone(), score=self.score[:g["T8p"]].clone())
             elif what == "select_median":

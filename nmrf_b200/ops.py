@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import GemmArgs, SeedWeights, lib
+from ._lib import GemmArgs, MlpArgs, SeedWeights, lib
 
 
 def _chk(t, name, dtype=torch.float32):
@@ -74,6 +74,53 @@ def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=N
     a.W_lo = _p(W_lo)
     a.Wt_hi, a.Wt_lo = (_p(Wt[0]), _p(Wt[1])) if Wt is not None else (None, None)
     _lib.check(lib.nmrf_token_gemm(ctypes.byref(a), _stream()), "token_gemm")
+    return Y
+
+
+def _tile_images(T):
+    """T [U,128,32] fp32 (device) -> [U, 8192]: per tile the SWIZZLE_128B image of hi = rna_tf32(T) (4096 floats) followed
+    by the image of lo = rna_tf32(T - hi).  Image: the 16-byte chunk c of row r sits at chunk position c ^ (r & 7)."""
+    T = T.contiguous()
+    hi, lo = torch.empty_like(T), torch.empty_like(T)
+    _lib.check(lib.nmrf_split_tf32(T.data_ptr(), hi.data_ptr(), lo.data_ptr(), T.numel(), _stream()), "split_tf32")
+    r = torch.arange(128, device=T.device)[:, None]
+    src = torch.arange(8, device=T.device)[None, :] ^ (r & 7)          # out[r, p] = in[r, p ^ (r & 7)]
+    img = lambda x: x.view(-1, 128, 8, 4)[:, r, src, :].reshape(-1, 4096)
+    return torch.cat([img(hi), img(lo)], 1).contiguous()
+
+
+def pack_mlp_stream(W1cat, Wfc1, Wfc2):
+    """Weight stream of nmrf_mlp_chain (P1 units, then F1(c,p), then F2(c,q); see nmrf_b200.h): W1cat [128, K1] (K1 % 32 == 0; for a block tail
+    [Wproj | I]), Wfc1 [512,128], Wfc2 [128,512] -> [K1/32 + 32, 8192] fp32."""
+    for n, t in (("W1cat", W1cat), ("Wfc1", Wfc1), ("Wfc2", Wfc2)):
+        _chk(t, n)
+    assert W1cat.shape[0] == 128 and W1cat.shape[1] % 32 == 0 and Wfc1.shape == (512, 128) and Wfc2.shape == (128, 512)
+    p1 = [W1cat[:, 32 * j:32 * j + 32] for j in range(W1cat.shape[1] // 32)]
+    f1 = lambda c: [torch.cat([Wfc1[64 * c:64 * c + 64, 64 * p:64 * p + 32], Wfc1[64 * c:64 * c + 64, 64 * p + 32:64 * p + 64]], 0)
+                    for p in range(2)]
+    f2 = lambda c: [Wfc2[:, 64 * c + 32 * q:64 * c + 32 * q + 32] for q in range(2)]
+    units = p1 + [u for c in range(8) for u in f1(c)] + [u for c in range(8) for u in f2(c)]
+    return _tile_images(torch.stack(units, 0))
+
+
+def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None):
+    """Y = x1 + fc2(GELU(fc1(LN(x1)))) + b_fc2 with x1 = concat(X, E) @ W1cat.T + bias_mid (bias_out = bias_mid + b_fc2);
+    wstream from pack_mlp_stream.  `out` may alias E."""
+    for n, t in (("X", X), ("E", E), ("wstream", wstream), ("bias_mid", bias_mid), ("gamma", ln[0]), ("beta", ln[1]), ("b1", b1),
+                 ("bias_out", bias_out)):
+        _chk(t, n)
+    rows, Kx = X.shape
+    Ke = E.shape[1] if E is not None else 0
+    if wstream.shape != ((Kx + Ke) // 32 + 32, 8192):
+        raise RuntimeError(f"wstream has shape {tuple(wstream.shape)}, expected {((Kx + Ke) // 32 + 32, 8192)}")
+    Y = out if out is not None else torch.empty(rows, 128, device=X.device, dtype=torch.float32)
+    a = MlpArgs()
+    a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), Kx
+    a.E, a.lde, a.Ke = _p(E), (E.stride(0) if E is not None else 0), Ke
+    a.Wstream, a.bias_mid, a.ln_gamma, a.ln_beta = wstream.data_ptr(), bias_mid.data_ptr(), ln[0].data_ptr(), ln[1].data_ptr()
+    a.b1, a.bias_out = b1.data_ptr(), bias_out.data_ptr()
+    a.Y, a.ldy, a.rows = Y.data_ptr(), Y.stride(0), rows
+    _lib.check(lib.nmrf_mlp_chain(ctypes.byref(a), _stream()), "mlp_chain")
     return Y
 
 

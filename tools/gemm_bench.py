@@ -35,3 +35,20 @@ for name, rows, Kx, Ke, N, ln, act, r in [("qkv", 34560, 128, 32, 384, True, 0, 
     units = ((rows + 127) // 128) * ((N + 127) // 128) * ((Kx + Ke + 31) // 32)
     res.append(f"{name} {us:6.1f}us ({us * 1.9e3 * 148 / units:5.0f} cyc/unit/SM)")
 print(f"DBG={os.environ.get('NMRF_B200_DBG', '0'):>2s} V={os.environ.get('NMRF_B200_GEMM_V', '6')}:  " + "  ".join(res))
+
+# fused block tail (nmrf_mlp_chain): proj + residual + LN2 + fc1 + GELU + fc2 in one launch
+for rows in (34560, 32640):
+    att, x = torch.randn(rows, 128, generator=g).to(dev), torch.randn(rows, 128, generator=g).to(dev)
+    Wp, W1, W2 = (torch.randn(128, 128, generator=g) / 11).to(dev), (torch.randn(512, 128, generator=g) / 11).to(dev), (torch.randn(128, 512, generator=g) / 22).to(dev)
+    ws = ops.pack_mlp_stream(torch.cat([Wp, torch.eye(128, device=dev)], 1).contiguous(), W1, W2)
+    z, o, b1 = torch.zeros(128, device=dev), torch.ones(128, device=dev), torch.zeros(512, device=dev)
+    for _ in range(3):
+        ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x)
+    e.record(); torch.cuda.synchronize()
+    us = s.elapsed_time(e) * 1e3 / reps
+    units = ((rows + 127) // 128) * 40
+    print(f"mlp_chain rows={rows}: {us:6.1f}us ({us * 1.9e3 * 148 / units:5.0f} cyc/unit/SM; replaces proj+fc1+fc2)")

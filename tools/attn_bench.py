@@ -26,3 +26,16 @@ for name, (B, Hp, Wp, K, ws, shift, se) in {"infer 1/8": (1, 72, 120, 4, 6, 3, T
     d = (res[0][1] - res[1][1]).abs().max().item() / res[0][1].abs().max().item()
     print(f"window {name}: simt {res[0][0]:.1f} us, mma {res[1][0]:.1f} us, max rel diff {d:.2e}")
 _lib.check(_lib.lib.nmrf_set_attention_impl(1), "impl")
+
+# stripe attention (propagation stack): 68 x 120 grid, K = 4
+B, h, w, K = 1, 68, 120, 4
+qkv = torch.randn(B * h * w * K, 384, generator=g).cuda()
+gv0, gv1 = (0.2 * torch.randn(64, 1, 3, 3, generator=g)).cuda(), (0.2 * torch.randn(64, 1, 3, 3, generator=g)).cuda()
+res = {}
+for impl in (0, 1):
+    _lib.check(_lib.lib.nmrf_set_attention_impl(impl), "impl")
+    out = ops.stripe_attention(qkv, B, h, w, K, gv0, gv1)
+    res[impl] = (timeit(lambda: ops.stripe_attention(qkv, B, h, w, K, gv0, gv1)), out)
+d = (res[0][1] - res[1][1]).abs().max().item() / res[0][1].abs().max().item()
+print(f"stripe 68x120 K=4: simt {res[0][0]:.1f} us, tcgen05 {res[1][0]:.1f} us, max rel diff {d:.2e}")
+_lib.check(_lib.lib.nmrf_set_attention_impl(1), "impl")

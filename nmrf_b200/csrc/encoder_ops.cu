@@ -13,7 +13,7 @@ namespace nmrf {
 namespace {
 using tc::rna_tf32_fast;
 
-constexpr int ST_PIX = 64;     // pixels per thread in the statistics pass (fp32 partial sums stay short)
+constexpr int ST_PIX = 16;     // pixels per thread in the statistics pass (fp32 partial sums stay short; enough CTAs to fill HBM)
 
 // grid (chunks, N); block = (C/4) * ppb threads: thread -> (pixel lane, 4 channels)
 __global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C, double* __restrict__ stats) {
@@ -24,7 +24,7 @@ __global__ void instnorm_stats_kernel(const float* __restrict__ x, int HW, int C
   const long long p0 = (long long)blockIdx.x * ppb * ST_PIX;
   const float* base = x + ((size_t)n * HW) * C + c4 * 4;
   float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 4
+#pragma unroll 8
   for (int k = 0; k < ST_PIX; ++k) {
     const long long p = p0 + (long long)k * ppb + pl;
     if (p < HW) {
@@ -58,58 +58,68 @@ struct ApplyArgs {
   const float* x; const double* xs; const float* r; const double* rs;
   float* plain; float* cat3;
   int HW, C, relu_inner, relu_outer;
-  long long total4;                                 // N*HW*C/4
+  long long per_sample4;                            // HW*C/4
 };
+constexpr int AP_ITEMS = 4;                         // float4 items per thread
 
+// grid (chunks, N): a CTA works inside ONE sample, so the fp64 mean / rstd of the sample's channels are computed once per
+// CTA into shared memory (they used to be recomputed per thread and channel: two fp64 divisions and a square root for every
+// four outputs made this kernel compute-bound at 3 TB/s)
 __global__ void instnorm_apply_kernel(const ApplyArgs a) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.total4) return;
+  extern __shared__ float ms[];                     // mean_x[C] rstd_x[C] mean_r[C] rstd_r[C]
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    float m = 0.f, rs = 1.f;
+    if (a.xs) mean_rstd(a.xs + ((size_t)n * a.C + c) * 2, a.HW, m, rs);
+    ms[c] = m; ms[a.C + c] = rs;
+    m = 0.f; rs = 1.f;
+    if (a.rs) mean_rstd(a.rs + ((size_t)n * a.C + c) * 2, a.HW, m, rs);
+    ms[2 * a.C + c] = m; ms[3 * a.C + c] = rs;
+  }
+  __syncthreads();
   const int c4n = a.C >> 2;
-  const int c = (int)(i % c4n) * 4;
-  const long long pix = i / c4n;                    // n*HW + p
-  const int n = (int)(pix / a.HW);
-  float4 v = *reinterpret_cast<const float4*>(a.x + pix * a.C + c);
-  float o[4] = {v.x, v.y, v.z, v.w};
-  if (a.xs) {
+  const long long base = (long long)n * a.per_sample4;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float m, rs;
-      mean_rstd(a.xs + ((size_t)n * a.C + c + j) * 2, a.HW, m, rs);
-      o[j] = (o[j] - m) * rs;
+  for (int it = 0; it < AP_ITEMS; ++it) {
+    const long long li = ((long long)blockIdx.x * AP_ITEMS + it) * blockDim.x + threadIdx.x;
+    if (li >= a.per_sample4) break;
+    const int c = (int)(li % c4n) * 4;
+    const long long pix = (base + li) / c4n;        // n*HW + p
+    float4 v = *reinterpret_cast<const float4*>(a.x + pix * a.C + c);
+    float o[4] = {v.x, v.y, v.z, v.w};
+    if (a.xs) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = (o[j] - ms[c + j]) * ms[a.C + c + j];
     }
-  }
-  if (a.relu_inner) {
+    if (a.relu_inner) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
-  }
-  if (a.r) {
-    const float4 rv = *reinterpret_cast<const float4*>(a.r + pix * a.C + c);
-    float rr[4] = {rv.x, rv.y, rv.z, rv.w};
-    if (a.rs) {
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    if (a.r) {
+      const float4 rv = *reinterpret_cast<const float4*>(a.r + pix * a.C + c);
+      float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+      if (a.rs) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float m, rs;
-        mean_rstd(a.rs + ((size_t)n * a.C + c + j) * 2, a.HW, m, rs);
-        rr[j] = (rr[j] - m) * rs;
+        for (int j = 0; j < 4; ++j) rr[j] = (rr[j] - ms[2 * a.C + c + j]) * ms[3 * a.C + c + j];
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] += rr[j];
     }
+    if (a.relu_outer) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] += rr[j];
-  }
-  if (a.relu_outer) {
+      for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
+    }
+    if (a.plain) *reinterpret_cast<float4*>(a.plain + pix * a.C + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (a.cat3) {
+      float h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
-  }
-  if (a.plain) *reinterpret_cast<float4*>(a.plain + pix * a.C + c) = make_float4(o[0], o[1], o[2], o[3]);
-  if (a.cat3) {
-    float h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { h[j] = rna_tf32_fast(o[j]); l[j] = rna_tf32_fast(o[j] - h[j]); }
-    float* d = a.cat3 + pix * 3 * a.C + c;
-    const float4 h4 = make_float4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<float4*>(d) = h4;
-    *reinterpret_cast<float4*>(d + a.C) = make_float4(l[0], l[1], l[2], l[3]);
-    *reinterpret_cast<float4*>(d + 2 * a.C) = h4;
+      for (int j = 0; j < 4; ++j) { h[j] = rna_tf32_fast(o[j]); l[j] = rna_tf32_fast(o[j] - h[j]); }
+      float* d = a.cat3 + pix * 3 * a.C + c;
+      const float4 h4 = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(d) = h4;
+      *reinterpret_cast<float4*>(d + a.C) = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<float4*>(d + 2 * a.C) = h4;
+    }
   }
 }
 
@@ -148,8 +158,10 @@ int instnorm_apply(const float* x, const double* x_stats, const float* r, const 
   ApplyArgs a;
   a.x = x; a.xs = x_stats; a.r = r; a.rs = r_stats; a.plain = out_plain; a.cat3 = out_cat3;
   a.HW = HW; a.C = C; a.relu_inner = relu_inner; a.relu_outer = relu_outer;
-  a.total4 = (long long)N * HW * (C / 4);
-  instnorm_apply_kernel<<<(unsigned)((a.total4 + 255) / 256), 256, 0, stream>>>(a);
+  NMRF_REQUIRE(C <= 2048, "instnorm_apply: C=%d too large", C);
+  a.per_sample4 = (long long)HW * (C / 4);
+  const unsigned chunks = (unsigned)((a.per_sample4 + 256 * AP_ITEMS - 1) / (256 * AP_ITEMS));
+  instnorm_apply_kernel<<<dim3(chunks, N), 256, 4 * C * sizeof(float), stream>>>(a);
   count_launch();
   return check_launch("instnorm_apply");
 }

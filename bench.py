@@ -269,14 +269,24 @@ def main():
     dom = max(agg, key=lambda k: agg[k]["ms"])
     d = agg[dom]
     ai = d["flops"] / max(d["bytes"], 1.0)
-    if ai > 100.0:     # dense contraction: compare with the measured dense tensor peak
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    # the path's arithmetic is 3xTF32 (the 1e-3 EPE bar): its ceiling is 1/6 of the dense bf16 peak.  A kernel
+    # whose algorithmic intensity puts its HBM roofline above that ceiling is tensor-bound.
+    if ai * pk["hbm_gbs"] * 1e9 > pk["tf"] * 1e12 / 6.0:
         roof = {"kernel": dom, "bound": "tensor", "achieved": d["flops"] / (d["ms"] * 1e-3) / 1e12, "peak": pk["tf"],
-                "unit": "TFLOP/s", "traffic": None,
-                "note": f"peak = {pk['source']} bf16 cuBLAS burst; exact-fp32 arithmetic is required by the 1e-3 EPE bar "
-                        "(3xTF32 ceiling = peak/6, fp32 FMA ceiling ~ 75 TFLOP/s)"}
+                "unit": "TFLOP/s", "traffic": traffic,
+                "note": f"achieved = algorithmic 2*MAC flops / per-launch CUDA-event time; peak = {pk['source']} bf16 cuBLAS burst; "
+                        "the arithmetic is error-compensated 3xTF32 (fp32-accurate, required by the 1e-3 EPE bar): ceiling = peak/6",
+                "frac_of_3xtf32_ceiling": d["flops"] / (d["ms"] * 1e-3) / 1e12 / (pk["tf"] / 6.0)}
     else:
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["bytes"] / (d["ms"] * 1e-3) / 1e9, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "traffic": None, "note": f"peak = {pk['source']} copy bandwidth"}
+                "unit": "GB/s", "traffic": traffic, "note": f"peak = {pk['source']} copy bandwidth"}
     roof["frac"] = roof["achieved"] / roof["peak"]
     roof["launches"], roof["avg_launch_us"] = d["launches"], 1e3 * d["ms"] / d["launches"]
     roof["share_of_hot_path"] = d["ms"] / hot_ms

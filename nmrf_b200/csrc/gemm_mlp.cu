@@ -76,6 +76,44 @@ __device__ __forceinline__ uint32_t idesc_n(int n) {
 }
 __device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, float* v) { tmem_ld32(taddr, v); }
 
+// One hidden chunk on one of the 16 GELU workers (all producer and LN/store warps: 4 per TMEM lane quarter, worker j takes
+// accumulator columns 16 j .. 16 j + 15 of its row): h = GELU(fc1 + b1) -> hi / lo -> the swizzled A-operand tiles of fc2.
+// The fc1 accumulator is released right after the TMEM load; the hidden buffer is written once the fc2 MMAs of the previous
+// chunk have read it.
+__device__ __forceinline__ void gelu_worker(MSmem& sm, uint32_t tmem_lane, uint8_t* sH, int row, int j, uint32_t gc, const float* b1,
+                                            int lane, long long* tp) {
+  const int b = gc & 1;
+  mtrace(tp, 2048 + gc * 8 + 0);
+  mbar_wait_warp(&sm.acc1_full[b], (gc >> 1) & 1);
+  mtrace(tp, 2048 + gc * 8 + 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  float v[16];
+  tmem_ld16(tmem_lane + (uint32_t)(M_COL_X + b * 64 + j * 16), v);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive_m(&sm.acc1_empty[b]);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + b1[i]);
+  mtrace(tp, 2048 + gc * 8 + 2);
+  if (gc >= 1) mbar_wait_warp(&sm.h_free, (gc - 1) & 1);
+  mtrace(tp, 2048 + gc * 8 + 3);
+  uint8_t* hi_t = sH + (j >> 1) * M_TILE;
+  uint8_t* lo_t = hi_t + 2 * M_TILE;
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    float4 h, l;
+    h.x = rna_tf32_fast(v[c4 * 4]); h.y = rna_tf32_fast(v[c4 * 4 + 1]); h.z = rna_tf32_fast(v[c4 * 4 + 2]); h.w = rna_tf32_fast(v[c4 * 4 + 3]);
+    l.x = v[c4 * 4] - h.x; l.y = v[c4 * 4 + 1] - h.y; l.z = v[c4 * 4 + 2] - h.z; l.w = v[c4 * 4 + 3] - h.w;
+    const uint32_t so = swz(row, (j & 1) * 4 + c4);
+    *reinterpret_cast<float4*>(hi_t + so) = h;
+    *reinterpret_cast<float4*>(lo_t + so) = l;
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive_m(&sm.h_full);
+  mtrace(tp, 2048 + gc * 8 + 4);
+}
+
 __global__ void __launch_bounds__(M_BLOCK, 1)
 mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
   extern __shared__ __align__(1024) uint8_t dsm[];
@@ -103,8 +141,8 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
   if (tid == 0) {
     for (int i = 0; i < M_NB; ++i) { mbar_init(&sm.done[i], 1); mbar_init(&sm.full_b[i], 1); }
     mbar_init(&sm.p1_full, 1); mbar_init(&sm.aln_full, M_EPI_WARPS);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.acc1_full[i], 1); mbar_init(&sm.acc1_empty[i], M_EPI_WARPS); }
-    mbar_init(&sm.h_full, M_EPI_WARPS); mbar_init(&sm.h_free, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.acc1_full[i], 1); mbar_init(&sm.acc1_empty[i], M_EPI_WARPS + 8); }
+    mbar_init(&sm.h_full, M_EPI_WARPS + 8); mbar_init(&sm.h_free, 1);
     mbar_init(&sm.acc0_final, 1); mbar_init(&sm.acc0_empty, M_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -191,6 +229,10 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
       }
+      // phase 3: the producers are GELU workers 0 and 1 of their lane quarter
+      for (int c = 0; c < M_NCH; ++c)
+        gelu_worker(sm, tmem + a_lane, sH, a_row, warp >> 2, (uint32_t)(it * M_NCH + c),
+                    sm.b1 + ((c + rot) & 7) * M_CH + (warp >> 2) * 16, lane, nullptr);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == M_MMA_WARP) {
@@ -406,39 +448,9 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
       __syncwarp();
       if (lane == 0) mbar_arrive_m(&sm.aln_full);
       mtrace(tp, 3968 + it * 8 + 1);
-      // ---- hidden chunks: GELU(fc1 + b1) -> hi/lo -> shared memory (A operand of fc2) ----
-      for (int c = 0; c < M_NCH; ++c, ++gc) {
-        const int b = gc & 1;
-        mtrace(tp, 2048 + gc * 8 + 0);
-        mbar_wait_warp(&sm.acc1_full[b], (gc >> 1) & 1, (dbg & 16) ? 128 : 0);
-        mtrace(tp, 2048 + gc * 8 + 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!(dbg & 2048)) tmem_ld32(tmem + t_lane + (uint32_t)(M_COL_X + b * 64 + half * 32), v);
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_m(&sm.acc1_empty[b]);
-        const float* b1 = sm.b1 + ((c + rot) & 7) * M_CH + half * 32;
-        if (!(dbg & 1)) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_fast(v[j] + b1[j]);
-        }
-        mtrace(tp, 2048 + gc * 8 + 2);
-        if (gc >= 1) mbar_wait_warp(&sm.h_free, (gc - 1) & 1, (dbg & 16) ? 128 : 0);          // fc2 MMAs of the previous chunk have read the buffer
-        mtrace(tp, 2048 + gc * 8 + 3);
-#pragma unroll
-        for (int c8 = 0; c8 < ((dbg & 1) ? 0 : 8); ++c8) {
-          float4 h, l;
-          h.x = rna_tf32_fast(v[c8 * 4]); h.y = rna_tf32_fast(v[c8 * 4 + 1]); h.z = rna_tf32_fast(v[c8 * 4 + 2]); h.w = rna_tf32_fast(v[c8 * 4 + 3]);
-          l.x = v[c8 * 4] - h.x; l.y = v[c8 * 4 + 1] - h.y; l.z = v[c8 * 4 + 2] - h.z; l.w = v[c8 * 4 + 3] - h.w;
-          const uint32_t so = swz(row, c8);
-          *reinterpret_cast<float4*>(my_h_hi + so) = h;
-          *reinterpret_cast<float4*>(my_h_lo + so) = l;
-        }
-        if (!(dbg & 1024)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive_m(&sm.h_full);
-        mtrace(tp, 2048 + gc * 8 + 4);
-      }
+      // ---- hidden chunks: GELU(fc1 + b1) -> hi/lo -> shared memory (A operand of fc2); workers 2 and 3 of the quarter ----
+      for (int c = 0; c < M_NCH; ++c, ++gc)
+        gelu_worker(sm, tmem + t_lane, sH, row, 2 + half, gc, sm.b1 + ((c + rot) & 7) * M_CH + (2 + half) * 16, lane, tp);
       // ---- final: x = acc0 + (b_proj + b_fc2), columns 64 half..+64 of this warp's 32 rows, coalesced through the staging ----
       mbar_wait_warp(&sm.acc0_final, it & 1);
       mtrace(tp, 3968 + it * 8 + 2);

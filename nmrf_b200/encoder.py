@@ -90,12 +90,16 @@ class FusedEncoder:
         self.head1x1 = [_Gemm(h[3].weight[:, :, 0, 0]) for h in heads8]      # concatconv, gw, proj
         self.feat_dim = bb.conv2.out_channels
         self._ws = {}
+        # cuDNN algorithm choice for the k x k convolutions: heuristics (default, deterministic) or autotuned.  Autotuning is
+        # only switched on through `autotune()`, which VERIFIES that the tuned algorithms reproduce the heuristic ones'
+        # features (a Winograd/FFT pick would not keep the [hi|lo|hi] products exact)
+        self.cudnn_autotune = False
+        self.autotune_report = None
 
     # ---- kernels ---------------------------------------------------------------------------------
-    @staticmethod
-    def _conv(cat3_nhwc, w, stride, pad):
+    def _conv(self, cat3_nhwc, w, stride, pad):
         x = cat3_nhwc.permute(0, 3, 1, 2)                   # NCHW view of an NHWC buffer == channels_last
-        with torch.backends.cudnn.flags(enabled=True, benchmark=False, allow_tf32=True):
+        with torch.backends.cudnn.flags(enabled=True, benchmark=self.cudnn_autotune, allow_tf32=True):
             y = F.conv2d(x, w, None, stride, pad)
         if not y.is_contiguous(memory_format=torch.channels_last):
             y = y.contiguous(memory_format=torch.channels_last)
@@ -131,6 +135,24 @@ class FusedEncoder:
                 f8c=new(N, h8, w8, 3 * self.feat_dim),
                 hd4=new(N, h4, w4, 256), hd8=new(N, h8, w8, 384), dims=(h2, w2, h4, w4, h8, w8))
         return self._ws[key]
+
+    @torch.no_grad()
+    def autotune(self, img1, img2, plan, tol=2e-6):
+        """Let cuDNN benchmark its algorithms for this shape and keep them only if every tensor the hot path consumes agrees
+        with the heuristic algorithms' result to `tol` (relative to the tensor's max; fp32 accumulation order is all that may
+        differ).  Returns the report dict (also in self.autotune_report)."""
+        outs = lambda: [t.clone() for t in (plan.f1_8, plan.f2_8, plan.context, *plan.cc8, *plan.gw8, *plan.cc4, *plan.gw4)]
+        self.cudnn_autotune = False
+        self.run(img1, img2, plan)
+        ref = outs()
+        self.cudnn_autotune = True
+        self.run(img1, img2, plan)                             # first call benchmarks and caches the algorithms
+        self.run(img1, img2, plan)
+        worst = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-12)) for a, b in zip(outs(), ref))
+        ok = worst <= tol
+        self.cudnn_autotune = ok
+        self.autotune_report = {"enabled": ok, "max_rel_diff_vs_heuristic": worst, "tol": tol}
+        return self.autotune_report
 
     # ---- forward ---------------------------------------------------------------------------------
     @torch.no_grad()

@@ -310,6 +310,24 @@ class NMRF(nn.Module):
         plan.run()
         return self._outputs(plan, B)
 
+    @torch.no_grad()
+    def autotune_encoder(self, img1, img2):
+        """Verified cuDNN autotuning of the fused encoder's convolutions for this input shape (FusedEncoder.autotune)."""
+        self.forward_device(img1, img2)                                # builds the plan and the encoder
+        if self._encoder is None:
+            return None
+        B, _, H, W = img1.shape
+        d = self.divis_by
+        pad_h, pad_w = (((H // d) + 1) * d - H) % d, (((W // d) + 1) * d - W) % d
+        if pad_h or pad_w:
+            img1 = F.pad(img1, [0, pad_w, 0, pad_h], mode="replicate")
+            img2 = F.pad(img2, [0, pad_w, 0, pad_h], mode="replicate")
+        img1 = img1.contiguous(memory_format=torch.channels_last)
+        img2 = img2.contiguous(memory_format=torch.channels_last)
+        Hp_, Wp_ = img1.shape[-2:]
+        plan = self.plan_for(B, self.backbone.output_dim, Hp_ // 8, Wp_ // 8, H, W)
+        return self._encoder.autotune(img1, img2, plan)
+
     def _outputs(self, plan, B):
         K = self.num_proposals
         return {

@@ -157,3 +157,26 @@ def test_no_cpu_path_and_eval_only():
     model = model.cuda().train()
     with pytest.raises(RuntimeError, match="inference path only"):
         model({"img1": img1, "img2": img2})
+
+
+@pytest.mark.gpu
+def test_graph_runner_with_verified_conv_autotune():
+    """GraphedNMRF(autotune_convs=True): cuDNN-autotuned encoder convolutions are kept only if they reproduce the heuristic
+    algorithms' features; either way the graphed forward must match the eager forward."""
+    import nmrf_b200
+    from nmrf_b200.runner import GraphedNMRF
+    from nmrf_b200.synthetic import synthetic_pair, synthetic_state_dict
+    cfg = nmrf_b200.get_cfg()
+    cfg.DPN.MAX_DISP, cfg.DPN.NUM_PROPOSALS = 64, 2
+    cfg.NMP.NUM_PROP_LAYERS = cfg.NMP.NUM_INFER_LAYERS = cfg.NMP.NUM_REFINE_LAYERS = 1
+    model = nmrf_b200.build_model(cfg).eval()
+    model.load_state_dict(synthetic_state_dict(model.state_dict(), 0, "reference"))
+    model = model.to("cuda:0")
+    img1, img2 = (t.cuda() for t in synthetic_pair(1, 96, 160, 64, 3))
+    ref = model.forward_device(img1, img2)["disp"].clone()
+    runner = GraphedNMRF(model, 1, 96, 160, autotune_convs=True, tune_images=(img1, img2))
+    rep = runner.autotune_report
+    assert rep is not None and rep["enabled"] == (rep["max_rel_diff_vs_heuristic"] <= rep["tol"])
+    out = runner(img1, img2)["disp"]
+    d = (out - ref).abs()
+    assert float(d.median()) <= 1e-4 and float((d <= 1e-3).float().mean()) >= 0.98

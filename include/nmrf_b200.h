@@ -235,6 +235,12 @@ int nmrf_instnorm_apply(const float* x, const double* x_stats, const float* r, c
                         float* out_plain, float* out_cat3, void* stream);
 /* x [rows, C] -> out [rows, 3C] = [hi | lo | hi] */
 int nmrf_split_cat3(const float* x, int64_t rows, int C, float* out, void* stream);
+/* left / right images [B,H,W,3] (the channels_last storage of [B,3,H,W]), values 0..255 -> [2B,H,W,9] = [hi | lo | hi] of
+ * 2 (x / 255) - 1 (nmrf/models/backbone.py:86): normalisation + batching + operand split of the stem convolution in one pass */
+int nmrf_image_prep(const float* img1_nhwc, const float* img2_nhwc, int B, int H, int W, float* out_cat3, void* stream);
+/* 2x2 average pool of an NHWC map [N,h,w,C] (backbone.py:96-98; h, w even are used, odd tails dropped like avg_pool2d):
+ * plain result split by sample half (out_a: samples 0..N/2-1, out_b: the rest) and its [hi | lo | hi] operand [N,h/2,w/2,3C] */
+int nmrf_avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_cat3, void* stream);
 
 #ifdef __cplusplus
 }

@@ -59,6 +59,8 @@ SIGNATURES = {
     "nmrf_instnorm_stats": [_P, _I, _I, _I, _P, _P],
     "nmrf_instnorm_apply": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
     "nmrf_split_cat3": [_P, c_int64, _I, _P, _P],
+    "nmrf_image_prep": [_P, _P, _I, _I, _I, _P, _P],
+    "nmrf_avgpool2_split": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "nmrf_set_attention_impl": [_I],
     "nmrf_debug_set_trace": [_P],
     "nmrf_pack_weight_tiles": [_P, _I, _I, _P, _P, _P],

@@ -46,6 +46,8 @@ bool window_attention_mma_supported(int K, int ws);
 int instnorm_stats(const float*, int, int, int, double*, cudaStream_t);
 int instnorm_apply(const float*, const double*, const float*, const double*, int, int, int, int, int, float*, float*, cudaStream_t);
 int split_cat3(const float*, long long, int, float*, cudaStream_t);
+int image_prep(const float*, const float*, int, int, int, float*, cudaStream_t);
+int avgpool2_split(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
 int window_attention_mma(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int,
                     int, int, float, float*, float*, cudaStream_t);
@@ -183,6 +185,12 @@ int nmrf_instnorm_apply(const float* x, const double* x_stats, const float* r, c
 }
 int nmrf_split_cat3(const float* x, int64_t rows, int C, float* out, void* stream) {
   return split_cat3(x, (long long)rows, C, out, ST(stream));
+}
+int nmrf_image_prep(const float* img1_nhwc, const float* img2_nhwc, int B, int H, int W, float* out_cat3, void* stream) {
+  return image_prep(img1_nhwc, img2_nhwc, B, H, W, out_cat3, ST(stream));
+}
+int nmrf_avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_cat3, void* stream) {
+  return avgpool2_split(x, N, h, w, C, out_a, out_b, out_cat3, ST(stream));
 }
 int nmrf_select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K, int Hp,
                        int Wp, int top, int left, float* disp_curr, void* stream) {

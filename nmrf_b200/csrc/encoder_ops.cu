@@ -133,7 +133,72 @@ __global__ void split_cat3_kernel(const float* __restrict__ x, long long rows, i
   float* d = out + r * 3 * C + c;
   d[0] = h; d[C] = l; d[2 * C] = h;
 }
+
+// images [B,H,W,3] (channels_last storage of the reference's [B,3,H,W] tensors), left then right -> [2B,H,W,9] =
+// [hi | lo | hi] of 2 (x / 255) - 1 (backbone.py:86), the operand of the stem convolution
+__global__ void image_prep_kernel(const float* __restrict__ img1, const float* __restrict__ img2, long long per_img, long long total,
+                                  float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // pixel index over both images
+  if (i >= total) return;
+  const float* src = (i < per_img ? img1 + i * 3 : img2 + (i - per_img) * 3);
+  float* d = out + i * 9;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float v = 2.f * __fdiv_rn(src[c], 255.f) - 1.f;
+    const float h = rna_tf32_fast(v), l = rna_tf32_fast(v - h);
+    d[c] = h; d[3 + c] = l; d[6 + c] = h;
+  }
+}
+
+// 2x2 average pool of an NHWC map (backbone.py:96-98) -> plain halves (first N/2 samples to out_a, the rest to out_b: the hot
+// path's f1_8 / f2_8) and the [hi | lo | hi] operand of the heads' 3x3 convolution; thread = 4 channels of one output pixel
+__global__ void avgpool2_split_kernel(const float* __restrict__ x, int N, int h, int w, int C, float* __restrict__ out_a,
+                                      float* __restrict__ out_b, float* __restrict__ cat3) {
+  const int c4n = C >> 2, ho = h >> 1, wo = w >> 1;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)N * ho * wo * c4n;
+  if (i >= total) return;
+  const int c = (int)(i % c4n) * 4;
+  long long p = i / c4n;
+  const int xo = (int)(p % wo); p /= wo;
+  const int yo = (int)(p % ho);
+  const int n = (int)(p / ho);
+  const float* s = x + (((size_t)n * h + 2 * yo) * w + 2 * xo) * C + c;
+  const float4 a = *reinterpret_cast<const float4*>(s), b = *reinterpret_cast<const float4*>(s + C);
+  const float4 e = *reinterpret_cast<const float4*>(s + (size_t)w * C), f = *reinterpret_cast<const float4*>(s + (size_t)w * C + C);
+  float o[4] = {((a.x + b.x) + (e.x + f.x)) * 0.25f, ((a.y + b.y) + (e.y + f.y)) * 0.25f, ((a.z + b.z) + (e.z + f.z)) * 0.25f,
+                ((a.w + b.w) + (e.w + f.w)) * 0.25f};
+  const size_t pix = ((size_t)n * ho + yo) * wo + xo;
+  const int half = N >> 1;
+  float* plain = n < half ? out_a + pix * C + c : out_b + (pix - (size_t)half * ho * wo) * C + c;
+  *reinterpret_cast<float4*>(plain) = make_float4(o[0], o[1], o[2], o[3]);
+  float hh[4], ll[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { hh[j] = rna_tf32_fast(o[j]); ll[j] = rna_tf32_fast(o[j] - hh[j]); }
+  float* d = cat3 + pix * 3 * C + c;
+  const float4 h4 = make_float4(hh[0], hh[1], hh[2], hh[3]);
+  *reinterpret_cast<float4*>(d) = h4;
+  *reinterpret_cast<float4*>(d + C) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+  *reinterpret_cast<float4*>(d + 2 * C) = h4;
+}
 }  // namespace
+
+int image_prep(const float* img1, const float* img2, int B, int H, int W, float* out, cudaStream_t stream) {
+  NMRF_REQUIRE(img1 && img2 && out && B > 0 && H > 0 && W > 0, "image_prep: bad arguments");
+  const long long per = (long long)B * H * W, total = 2 * per;
+  image_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img1, img2, per, total, out);
+  count_launch();
+  return check_launch("image_prep");
+}
+
+int avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* cat3, cudaStream_t stream) {
+  NMRF_REQUIRE(x && out_a && out_b && cat3, "avgpool2_split: null pointer");
+  NMRF_REQUIRE(N > 0 && N % 2 == 0 && h >= 2 && w >= 2 && C % 4 == 0, "avgpool2_split: N=%d h=%d w=%d C=%d", N, h, w, C);
+  const long long total = (long long)N * (h / 2) * (w / 2) * (C / 4);
+  avgpool2_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, N, h, w, C, out_a, out_b, cat3);
+  count_launch();
+  return check_launch("avgpool2_split");
+}
 
 int instnorm_stats(const float* x, int N, int HW, int C, double* stats, cudaStream_t stream) {
   NMRF_REQUIRE(x && stats && N > 0 && HW > 0, "instnorm_stats: bad arguments");

@@ -157,10 +157,9 @@ class FusedEncoder:
     # ---- forward ---------------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, img1, img2, plan):
-        B = img1.shape[0]
-        x = torch.cat((img1, img2), 0)
-        N, _, H, W = x.shape
-        ws = self._workspace(N, H, W, x.device)
+        B, _, H, W = img1.shape
+        N = 2 * B
+        ws = self._workspace(N, H, W, img1.device)
         h2, w2, h4, w4, h8, w8 = ws["dims"]
         stats = ws["stats"]
         stats.zero_()
@@ -170,8 +169,11 @@ class FusedEncoder:
             i = next(si)
             return stats[i].reshape(-1)[: N * C * 2].view(N, C, 2)
 
-        x = (2 * (x / 255.0) - 1.0).permute(0, 2, 3, 1).contiguous()          # backbone.py:86, NHWC
-        _lib.check(lib.nmrf_split_cat3(x.data_ptr(), N * H * W, 3, ws["img"].data_ptr(), _stream()), "split_cat3")
+        # backbone.py:86 normalisation, left/right batching and the hi/lo split of the stem operand in one pass; the images are
+        # channels_last, i.e. already NHWC in memory
+        i1 = img1.permute(0, 2, 3, 1).contiguous()
+        i2 = img2.permute(0, 2, 3, 1).contiguous()
+        _lib.check(lib.nmrf_image_prep(i1.data_ptr(), i2.data_ptr(), B, H, W, ws["img"].data_ptr(), _stream()), "image_prep")
         y = self._conv(ws["img"], self.stem, 2, 3)
         s = st(64); self._stats(y, s)
         P, C3 = ws["p2"], ws["c2"]
@@ -203,15 +205,14 @@ class FusedEncoder:
         # 1x1 output convolution (with bias) -> feat @1/4, NHWC; feat @1/8 = avg_pool2 (backbone.py:96-98)
         rows4 = N * h4 * w4
         self.out(plain.data_ptr(), plain.shape[-1], rows4, ws["feat4"].data_ptr(), self.feat_dim)
-        feat8 = F.avg_pool2d(ws["feat4"].permute(0, 3, 1, 2), 2, 2).permute(0, 2, 3, 1)
-        if not feat8.is_contiguous():
-            feat8 = feat8.contiguous()
-        plan.f1_8.copy_(feat8[:B]); plan.f2_8.copy_(feat8[B:])
+        _lib.check(lib.nmrf_avgpool2_split(ws["feat4"].data_ptr(), N, h4, w4, self.feat_dim, plan.f1_8.data_ptr(), plan.f2_8.data_ptr(),
+                                           ws["f8c"].data_ptr(), _stream()), "avgpool2_split")
         # heads: one 3x3 convolution for all heads of a scale, InstanceNorm + ReLU, then the 1x1 projections as GEMMs
-        for scale, feat, f3, hd, hh, ww, cc, gw in ((8, feat8, ws["f8c"], ws["hd8"], h8, w8, plan.cc8, plan.gw8),
+        for scale, feat, f3, hd, hh, ww, cc, gw in ((8, None, ws["f8c"], ws["hd8"], h8, w8, plan.cc8, plan.gw8),
                                                     (4, ws["feat4"], ws["f4c"], ws["hd4"], h4, w4, plan.cc4, plan.gw4)):
             rows = N * hh * ww
-            _lib.check(lib.nmrf_split_cat3(feat.data_ptr(), rows, self.feat_dim, f3.data_ptr(), _stream()), "split_cat3")
+            if feat is not None:                             # the 1/8 operand was written by the pooling kernel
+                _lib.check(lib.nmrf_split_cat3(feat.data_ptr(), rows, self.feat_dim, f3.data_ptr(), _stream()), "split_cat3")
             y = self._conv(f3, self.head3x3[scale], 1, 1)
             C = y.shape[-1]
             s = st(C); self._stats(y, s)

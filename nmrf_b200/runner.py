@@ -53,6 +53,64 @@ class GraphedNMRF:
         self.hot_graph.replay()
         return self.plan.disp
 
+    # ---- streaming API: host pairs in, host disparities out, copies overlapped with the previous / next pair's compute ----
+    def _pipeline_init(self):
+        dev = self.img1.device
+        self._copy = torch.cuda.Stream(device=dev)
+        self._stage_in = [(torch.empty_like(self.img1), torch.empty_like(self.img2)) for _ in range(2)]
+        self._stage_out = [torch.empty_like(self.out["disp"]) for _ in range(2)]
+        self._host_out = [torch.empty(self.out["disp"].shape, pin_memory=True) for _ in range(2)]
+        ev = lambda: torch.cuda.Event()
+        self._ev_h2d, self._ev_in_free, self._ev_done, self._ev_d2h = ([ev(), ev()] for _ in range(4))
+        self._seq = 0
+        self._primed = False
+
+    def _prefetch(self, slot, img1, img2):
+        with torch.cuda.stream(self._copy):
+            self._copy.wait_event(self._ev_in_free[slot])          # the d2d copy that last read this staging pair is done
+            self._stage_in[slot][0].copy_(img1, non_blocking=True)
+            self._stage_in[slot][1].copy_(img2, non_blocking=True)
+            self._ev_h2d[slot].record(self._copy)
+
+    def stream(self, pairs):
+        """Generator over (img1, img2) HOST pairs (pinned memory): yields each pair's disparity as a pinned host tensor that stays
+        valid until the next-but-one result is produced.  The H2D copy of pair i+1 and the D2H copy of pair i-1 run on a copy
+        stream while pair i computes (the graph itself is unchanged: staging buffers are copied device-to-device)."""
+        if not hasattr(self, "_copy"):
+            self._pipeline_init()
+        main = torch.cuda.current_stream(self.img1.device)
+        it = iter(pairs)
+        nxt = next(it, None)
+        if nxt is None:
+            return
+        for e in self._ev_in_free + self._ev_d2h:
+            e.record(main)
+        self._prefetch(self._seq & 1, *nxt)
+        pending = None
+        while nxt is not None:
+            slot = self._seq & 1
+            cur, nxt = nxt, next(it, None)
+            if nxt is not None:
+                self._prefetch(slot ^ 1, *nxt)
+            main.wait_event(self._ev_h2d[slot])
+            self.img1.copy_(self._stage_in[slot][0]); self.img2.copy_(self._stage_in[slot][1])
+            self._ev_in_free[slot].record(main)
+            self.graph.replay()
+            main.wait_event(self._ev_d2h[slot])                      # the D2H that last read this output staging buffer is done
+            self._stage_out[slot].copy_(self.out["disp"])
+            self._ev_done[slot].record(main)
+            with torch.cuda.stream(self._copy):
+                self._copy.wait_event(self._ev_done[slot])
+                self._host_out[slot].copy_(self._stage_out[slot], non_blocking=True)
+                self._ev_d2h[slot].record(self._copy)
+            if pending is not None:
+                self._ev_d2h[pending].synchronize()
+                yield self._host_out[pending]
+            pending = slot
+            self._seq += 1
+        self._ev_d2h[pending].synchronize()
+        yield self._host_out[pending]
+
     def __call__(self, img1, img2, to_host=False):
         self.img1.copy_(img1, non_blocking=True)
         self.img2.copy_(img2, non_blocking=True)

@@ -180,3 +180,8 @@ def test_graph_runner_with_verified_conv_autotune():
     out = runner(img1, img2)["disp"]
     d = (out - ref).abs()
     assert float(d.median()) <= 1e-4 and float((d <= 1e-3).float().mean()) >= 0.98
+    # streaming API: host pairs in, host disparities out, copies overlapped; same numbers as the blocking call, in order
+    pairs = [tuple(t.pin_memory() for t in synthetic_pair(1, 96, 160, 64, 10 + i)) for i in range(5)]
+    want = [runner(a, b)["disp"].cpu().clone() for a, b in pairs]
+    got = [o.clone() for o in runner.stream(pairs)]
+    assert len(got) == 5 and all(torch.equal(g, w) for g, w in zip(got, want))

@@ -81,9 +81,9 @@ int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float*
  *                                                                    residual stream x in E, so the add happens in the tensor core)
  *   Y  = x1 + fc2( GELU( fc1( LN(x1) ) ) ) + b_fc2                   (x + Mlp(norm2(x)), NMP.py:362-363,572-573; timm Mlp 128->512->128)
  * Wstream: (Kx+Ke)/32 + 32 units of 8192 floats (16 KB hi image + 16 KB lo image, SWIZZLE_128B shared-memory images of
- * [128 x 32] fp32 tiles):  P1(0..n1-1), then F1(c,p) at n1 + 2c + p, then F2(c,q) at n1 + 16 + 2c + q (c = hidden chunk of 64,
- * 0..7; every CTA walks the k-blocks and the chunks starting from its own rotation, so the fp32 summation order differs per
- * tile):  P1(j)[n,k] = W1cat[n, 32j+k];  F1(c,p)[r,k] = Wfc1[64c + r%64, 32(2p + r/64) + k];  F2(c,q)[n,k] = Wfc2[n, 64c+32q+k]
+ * [128 x 32] fp32 tiles):  P1(0..n1-1), then F1(c) at n1 + c, then F2(c) at n1 + 16 + c (c = hidden chunk of 32, 0..15; every
+ * CTA walks the k-blocks and the chunks starting from its own rotation, so the fp32 summation order differs per tile):
+ * P1(j)[n,k] = W1cat[n, 32j+k];  F1(c)[r,k] = Wfc1[32c + r%32, 32(r/32) + k];  F2(c)[n,k] = Wfc2[n, 32c+k]
  * (nmrf_b200/hotpath.py: pack_mlp_stream).  bias_out = bias_mid + b_fc2.  Kx+Ke must be a multiple of 32 (<= 512);
  * Y may alias E (each tile is read completely before it is written).  Same 3xTF32 arithmetic as nmrf_token_gemm. */
 typedef struct {

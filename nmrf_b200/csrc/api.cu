@@ -32,7 +32,6 @@ int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stre
 int gemm6_set_trace(long long* dev_ptr);
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
 int mlp_set_trace(long long* dev_ptr);
-int mlp_chain2(const nmrf_mlp_args& a, cudaStream_t stream);
 int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
@@ -115,9 +114,6 @@ int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream) {
   NMRF_REQUIRE((a->Ke == 0) == (a->E == nullptr), "mlp_chain: E/Ke mismatch");
   NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldy % 4 == 0 && (a->Ke == 0 || a->lde % 4 == 0), "mlp_chain: bad leading dimension");
   if (a->rows == 0) return NMRF_OK;
-  // NMRF_B200_MLP2=1: the CTA-pair (tcgen05 cta_group::2) schedule of the same arithmetic (gemm_mlp2.cu)
-  static const int pair = [] { const char* e = getenv("NMRF_B200_MLP2"); return (e && e[0] == '1') ? 1 : 0; }();
-  if (pair) return mlp_chain2(*a, ST(stream));
   return mlp_chain(*a, ST(stream));
 }
 int nmrf_set_attention_impl(int tensor_cores) {

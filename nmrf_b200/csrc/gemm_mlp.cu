@@ -8,20 +8,27 @@
 // att + x in, x out and the weight stream.
 //
 //   tensor memory (512 columns):  [0,128) acc0: x1, later x1 + fc2(...)   [128,256) LN2(x1) hi   [256,384) LN2(x1) lo
-//                                 [384,512) phase 1: two A buffers (hi|lo of a 32-wide k-block); phase 3: two fc1 accumulators
-//                                 of 64 hidden columns each
+//                                 [384,512) phase 1: two A buffers (hi|lo of a 32-wide k-block); phase 3: FOUR fc1 accumulators
+//                                 of 32 hidden columns each
 //   shared memory:                weight ring 3 x 32 KB (every "unit" of the weight stream is a 16 KB hi image + a 16 KB lo
-//                                 image and 768 tensor cycles), GELU'd hidden chunk hi/lo [128 x 64] (64 KB, SS-mode A operand
-//                                 of fc2; doubles as the store staging of the final epilogue), raw-A ring 3 x 16 KB
-//   unit stream per tile:         P1(0..n1-1)   F1(0) F1(1) F2(0) F1(2) F2(1) ... F1(7) F2(6) F2(7), two units each:
-//                                 P1(j): k-block j of [Wproj | I] (128 x 32);  F1(c): fc1 rows 64c..64c+63 (64 x 128, two
-//                                 k-block pairs);  F2(c): fc2 columns 64c..64c+63 (128 x 64, two k-blocks).
-//                                 nmrf_b200/hotpath.py packs the stream in exactly this order (pack_mlp_stream).
-//   warps                         0-7 producers (phase-1 A operand: raw ring -> hi/lo split -> tcgen05.st, as gemm_tc6),
-//                                 8 MMA issuer, 9-16 LN / GELU / store warps (thread = row = TMEM lane), 17 TMA.
+//                                 image and 768 tensor cycles), TWO GELU'd hidden chunks hi/lo [128 x 32] (2 x 32 KB, SS-mode A
+//                                 operand of fc2; also the store staging of the final epilogue), raw-A ring 3 x 16 KB
+//   hidden chunks of 32:          fc1 runs three chunks ahead of fc2 (four accumulators), the hidden tile is double buffered, so
+//                                 the chain  fc1(c) -> GELU(c) -> fc2(c)  of one chunk overlaps the tensor work of its neighbours
+//                                 (with 64-wide chunks and one hidden buffer GELU + stores + fc2 were serialised: 5.4k cycles
+//                                 per 3.1k cycles of tensor work, tools/mlp_trace.py)
+//   unit stream per tile:         P1(0..n1-1)   F1(0) F1(1) F1(2)   [F1(c+3) F2(c)] c = 0..12   F2(13) F2(14) F2(15)
+//                                 P1(j): k-block j of [Wproj | I] (128 x 32);  F1(c): fc1 rows 32c..32c+31 (32 x 128, four
+//                                 k-block sub-images);  F2(c): fc2 columns 32c..32c+31 (128 x 32).
+//                                 nmrf_b200/ops.py: pack_mlp_stream lays the stream out as P1 | F1(0..15) | F2(0..15).
+//   warps                         0-7 producers (phase-1 A operand: raw ring -> hi/lo split -> tcgen05.st, as gemm_tc6) and GELU
+//                                 workers, 9-16 LN / GELU / store warps (thread = row = TMEM lane), 17 TMA, and TWO MMA issuers:
+//                                 warp 8 issues phase 1 and the fc2 units, warp 18 the fc1 units.  The tcgen05 issue queue holds
+//                                 only 2-3 MMAs (tools/probes/seq_probe.cu: 12 MMAs block the issuing thread for 600 of their 768
+//                                 cycles), so whatever one issuer spends between units (two barrier polls, elect, descriptors:
+//                                 ~500 cycles) is tensor idle time unless the other issuer's unit is executing meanwhile.
 // Arithmetic: 3xTF32 with RN hi / exact lo split as in gemm_tc6; LayerNorm two-pass in fp32 from the fp32
 // accumulator; GELU as gemm_tc6.
-#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,25 +39,29 @@ using namespace tc;
 constexpr int M_BM = 128, M_BK = 32, M_NB = 3, M_RAW = 3;
 constexpr int M_TILE = M_BM * M_BK * 4;            // 16 KB image
 constexpr int M_UNIT = 2 * M_TILE;                 // 32 KB: hi image + lo image
-constexpr int M_HID = 512, M_CH = 64, M_NCH = M_HID / M_CH;      // fc1 width, hidden chunk, chunks
-constexpr int M_PROD = 256, M_MMA_WARP = 8, M_EPI_WARP0 = 9, M_EPI_WARPS = 8, M_TMA_WARP = 17;
-constexpr int M_BLOCK = (M_TMA_WARP + 1) * 32;     // 576
+constexpr int M_HID = 512, M_CH = 32, M_NCH = M_HID / M_CH;      // fc1 width, hidden chunk, chunks (16)
+constexpr int M_AHEAD = 3;                         // fc1 runs this many chunks ahead of fc2
+constexpr int M_PROD = 256, M_MMA_WARP = 8, M_EPI_WARP0 = 9, M_EPI_WARPS = 8, M_TMA_WARP = 17, M_MMA2_WARP = 18;
+constexpr int M_WORKERS = M_EPI_WARPS + 8;         // GELU workers (warps)
+constexpr int M_BLOCK = (M_MMA2_WARP + 1) * 32;    // 608
 constexpr int M_HANDOFF = M_PROD + 32;
 constexpr int M_RAW_BAR = 5;
 constexpr int M_COL_ALN_HI = 128, M_COL_ALN_LO = 256, M_COL_X = 384;      // TMEM columns
+constexpr int M_ABUF = 4;                          // phase-1 A buffers (hi|lo of a k-block, 64 columns): [384,512) and [128,256)
+__device__ __forceinline__ uint32_t abuf_col(uint32_t b) { return b < 2 ? M_COL_X + 64 * b : M_COL_ALN_HI + 64 * (b - 2); }
 constexpr int M_OFF_H = M_NB * M_UNIT;             // 96 KB
-constexpr int M_OFF_RAW = M_OFF_H + 4 * M_TILE;    // + 64 KB
+constexpr int M_OFF_RAW = M_OFF_H + 4 * M_TILE;    // + 64 KB: hidden buffer b = [hi 16 KB | lo 16 KB] at M_OFF_H + b * 32 KB
 constexpr int M_DYN = M_OFF_RAW + M_RAW * M_TILE + 1024;
 
 struct MSmem {
   uint64_t done[M_NB];        // MMAs of the unit that used weight slot s are complete
   uint64_t full_b[M_NB];      // weight unit landed (expect_tx 32 KB)
   uint64_t p1_full;           // acc0 = x1 - b_proj is complete (commit)
-  uint64_t aln_full;          // LN2(x1) hi/lo are in TMEM (8 warp arrivals)
-  uint64_t acc1_full[2];      // fc1 chunk accumulator complete (commit)
-  uint64_t acc1_empty[2];     // ... drained (8 warp arrivals)
-  uint64_t h_full;            // hidden chunk hi/lo in shared memory (8 warp arrivals)
-  uint64_t h_free;            // fc2 MMAs of the chunk complete (commit)
+  uint64_t aln_full;          // LN2(x1) hi/lo are in TMEM (16 warp arrivals)
+  uint64_t acc1_full[4];      // fc1 chunk accumulator complete (commit)
+  uint64_t acc1_empty[4];     // ... drained (16 warp arrivals)
+  uint64_t h_full[2];         // hidden chunk hi/lo in shared memory (16 warp arrivals)
+  uint64_t h_free[2];         // fc2 MMAs of the chunk complete (commit)
   uint64_t acc0_final;        // all MMAs of the tile complete (commit)
   uint64_t acc0_empty;        // final epilogue has read acc0 (8 warp arrivals)
   uint32_t tmem_base;
@@ -59,14 +70,15 @@ struct MSmem {
   alignas(16) float bmid[128];
   alignas(16) float bout[128];
   alignas(16) float b1[M_HID];
+  float red[2][4][M_BM];      // LayerNorm partial sums: [pass][worker of the quarter][row]
 };
 
 __device__ __forceinline__ void mbar_arrive_m(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// optional cycle trace of CTA 0 (debug tooling, nmrf_debug_set_trace): MMA warp: unit g -> [g*4 + {0 before weight wait, 1 after,
-// 2 after issue}], 512 units max; LN/GELU warp 9: 2048 + chunk*8 + {0 before acc1_full, 1 after, 2 after GELU, 3 after h_free,
-// 4 after stores}; 3968 + tile*8 + {0 p1_full seen, 1 LN done, 2 acc0_final seen, 3 stored}
+// optional cycle trace of CTA 0 (debug tooling, nmrf_debug_set_trace; tools/mlp_trace.py): MMA warp: unit g -> g*4 + {0 before the
+// weight wait, 1 after, 2 after issue, 3 after the hand-off barrier (phase 1)}; GELU warp 9: 2048 + chunk*8 + {0 before acc1_full,
+// 1 after, 2 after GELU, 3 after h_free, 4 after stores}; 3968 + tile*8 + {0 p1_full seen, 1 LN done, 2 acc0_final seen, 3 stored}
 __device__ long long* g_trace_m = nullptr;
 __device__ __forceinline__ void mtrace(long long* tp, int idx) {
   if (tp && idx < 4096) tp[idx] = clock64();
@@ -74,65 +86,103 @@ __device__ __forceinline__ void mtrace(long long* tp, int idx) {
 __device__ __forceinline__ uint32_t idesc_n(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld32_raw(uint32_t taddr, float* v) { tmem_ld32(taddr, v); }
 
-// One hidden chunk on one of the 16 GELU workers (all producer and LN/store warps: 4 per TMEM lane quarter, worker j takes
-// accumulator columns 16 j .. 16 j + 15 of its row): h = GELU(fc1 + b1) -> hi / lo -> the swizzled A-operand tiles of fc2.
-// The fc1 accumulator is released right after the TMEM load; the hidden buffer is written once the fc2 MMAs of the previous
-// chunk have read it.
-__device__ __forceinline__ void gelu_worker(MSmem& sm, uint32_t tmem_lane, uint8_t* sH, int row, int j, uint32_t gc, const float* b1,
-                                            int lane, long long* tp) {
-  const int b = gc & 1;
-  mtrace(tp, 2048 + gc * 8 + 0);
-  mbar_wait_warp(&sm.acc1_full[b], (gc >> 1) & 1);
-  mtrace(tp, 2048 + gc * 8 + 1);
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  float v[16];
-  tmem_ld16(tmem_lane + (uint32_t)(M_COL_X + b * 64 + j * 16), v);
+// LN2 of x1 = acc0 + b_proj on the 16 worker warps: thread = row (TMEM lane), worker j of the lane quarter owns columns
+// 32 j .. 32 j + 31.  Two-pass like torch (mean, then squared deviations); the four workers of a quarter exchange their
+// partial sums through shared memory (named barrier 8 + quarter, 128 threads).  Result: hi / lo of the normalised row as the
+// A operand of fc1 in TMEM.
+__device__ __forceinline__ void ln_worker(MSmem& sm, uint32_t tmem_lane, int q, int row, int j, int lane) {
+  float v[32];
+  tmem_ld32(tmem_lane + (uint32_t)(j * 32), v);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[i] += sm.bmid[j * 32 + i]; s += v[i]; }
+  sm.red[0][j][row] = s;
+  asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(128) : "memory");
+  const float mean = ((sm.red[0][0][row] + sm.red[0][1][row]) + (sm.red[0][2][row] + sm.red[0][3][row])) * (1.f / 128.f);
+  float qq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; qq = fmaf(d, d, qq); }
+  sm.red[1][j][row] = qq;
+  asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(128) : "memory");
+  const float var = ((sm.red[1][0][row] + sm.red[1][1][row]) + (sm.red[1][2][row] + sm.red[1][3][row])) * (1.f / 128.f);
+  const float rstd = 1.f / sqrtf(var + 1e-5f);
+  uint32_t hi[32], lo[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int k = j * 32 + i;
+    const float y = (v[i] - mean) * rstd * sm.gamma[k] + sm.beta[k];
+    const float h = rna_tf32_fast(y);
+    hi[i] = __float_as_uint(h);
+    lo[i] = __float_as_uint(y - h);
+  }
+  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32), hi);
+  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32 + 16), hi + 16);
+  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_LO + j * 32), lo);
+  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_LO + j * 32 + 16), lo + 16);
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
-  if (lane == 0) mbar_arrive_m(&sm.acc1_empty[b]);
+  if (lane == 0) mbar_arrive_m(&sm.aln_full);
+}
+
+// One hidden chunk (32 columns) on one of the 16 GELU workers (all producer and LN/store warps: 4 per TMEM lane quarter, worker j
+// takes accumulator columns 8 j .. 8 j + 7 of its row): h = GELU(fc1 + b1) -> hi / lo -> the swizzled A-operand tile of fc2.
+// The fc1 accumulator is released right after the TMEM load; the hidden buffer gc & 1 is written once the fc2 MMAs of chunk
+// gc - 2 have read it.
+__device__ __forceinline__ void gelu_worker(MSmem& sm, uint32_t tmem_lane, uint8_t* sH, int row, int j, uint32_t gc, const float* b1,
+                                            int lane, long long* tp) {
+  const int ab = gc & 3, hb = gc & 1;
+  mtrace(tp, 2048 + gc * 8 + 0);
+  mbar_wait_warp(&sm.acc1_full[ab], (gc >> 2) & 1);
+  mtrace(tp, 2048 + gc * 8 + 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  float v[8];
+  tmem_ld8(tmem_lane + (uint32_t)(M_COL_X + ab * M_CH + j * 8), v);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive_m(&sm.acc1_empty[ab]);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = gelu_fast(v[i] + b1[i]);
+  for (int i = 0; i < 8; ++i) v[i] = gelu_fast(v[i] + b1[i]);
   mtrace(tp, 2048 + gc * 8 + 2);
-  if (gc >= 1) mbar_wait_warp(&sm.h_free, (gc - 1) & 1);
+  if (gc >= 2) mbar_wait_warp(&sm.h_free[hb], ((gc >> 1) - 1) & 1);
   mtrace(tp, 2048 + gc * 8 + 3);
-  uint8_t* hi_t = sH + (j >> 1) * M_TILE;
-  uint8_t* lo_t = hi_t + 2 * M_TILE;
+  uint8_t* hi_t = sH + hb * M_UNIT;
+  uint8_t* lo_t = hi_t + M_TILE;
 #pragma unroll
-  for (int c4 = 0; c4 < 4; ++c4) {
+  for (int c2 = 0; c2 < 2; ++c2) {
     float4 h, l;
-    h.x = rna_tf32_fast(v[c4 * 4]); h.y = rna_tf32_fast(v[c4 * 4 + 1]); h.z = rna_tf32_fast(v[c4 * 4 + 2]); h.w = rna_tf32_fast(v[c4 * 4 + 3]);
-    l.x = v[c4 * 4] - h.x; l.y = v[c4 * 4 + 1] - h.y; l.z = v[c4 * 4 + 2] - h.z; l.w = v[c4 * 4 + 3] - h.w;
-    const uint32_t so = swz(row, (j & 1) * 4 + c4);
+    h.x = rna_tf32_fast(v[c2 * 4]); h.y = rna_tf32_fast(v[c2 * 4 + 1]); h.z = rna_tf32_fast(v[c2 * 4 + 2]); h.w = rna_tf32_fast(v[c2 * 4 + 3]);
+    l.x = v[c2 * 4] - h.x; l.y = v[c2 * 4 + 1] - h.y; l.z = v[c2 * 4 + 2] - h.z; l.w = v[c2 * 4 + 3] - h.w;
+    const uint32_t so = swz(row, j * 2 + c2);
     *reinterpret_cast<float4*>(hi_t + so) = h;
     *reinterpret_cast<float4*>(lo_t + so) = l;
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncwarp();
-  if (lane == 0) mbar_arrive_m(&sm.h_full);
+  if (lane == 0) mbar_arrive_m(&sm.h_full[hb]);
   mtrace(tp, 2048 + gc * 8 + 4);
 }
 
 __global__ void __launch_bounds__(M_BLOCK, 1)
-mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
+mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   __shared__ MSmem sm;
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
   auto sW = [&](int slot) { return base + slot * M_UNIT; };            // hi image at +0, lo image at +16 KB
-  uint8_t* sH = base + M_OFF_H;                                        // hi q0, hi q1, lo q0, lo q1 (16 KB each)
+  uint8_t* sH = base + M_OFF_H;                                        // two hidden buffers: [hi | lo] each
   auto sRaw = [&](int i) { return base + M_OFF_RAW + i * M_TILE; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long* const tp = (blockIdx.x == 0 && (tid == M_MMA_WARP * 32 || tid == M_EPI_WARP0 * 32)) ? g_trace_m : nullptr;
+  long long* const tp = (blockIdx.x == 0 && (tid == M_MMA_WARP * 32 || tid == M_MMA2_WARP * 32 || tid == M_EPI_WARP0 * 32)) ? g_trace_m : nullptr;
   const int Ktot = a.Kx + a.Ke;
   const int n1 = Ktot / M_BK;                      // phase-1 units per tile
-  const int upt = n1 + 4 * M_NCH;                  // units per tile
+  const int upt = n1 + 2 * M_NCH;                  // units per tile
   const int tstep = gridDim.x;
-  // Every CTA walks the same weight stream; in lockstep all 148 of them would pull the same 32 KB out of the same few L2
-  // slices at the same time (measured: 7-8k cycles per bulk copy).  Each CTA therefore starts at its own rotation of the
-  // k-block order (phase 1) and of the hidden-chunk order (phase 3); both are sums, so only the fp32 summation order moves.
-  const int rot = blockIdx.x & 7;
+  // every CTA starts at its own rotation of the k-block order (phase 1) and of the hidden-chunk order (phase 3), so that the
+  // 148 CTAs do not all pull the same 32 KB of the weight stream at the same time; both are sums: only the fp32 summation
+  // order depends on the CTA
+  const int rot = blockIdx.x & (M_NCH - 1);
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
@@ -140,9 +190,9 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
   }
   if (tid == 0) {
     for (int i = 0; i < M_NB; ++i) { mbar_init(&sm.done[i], 1); mbar_init(&sm.full_b[i], 1); }
-    mbar_init(&sm.p1_full, 1); mbar_init(&sm.aln_full, M_EPI_WARPS);
-    for (int i = 0; i < 2; ++i) { mbar_init(&sm.acc1_full[i], 1); mbar_init(&sm.acc1_empty[i], M_EPI_WARPS + 8); }
-    mbar_init(&sm.h_full, M_EPI_WARPS + 8); mbar_init(&sm.h_free, 1);
+    mbar_init(&sm.p1_full, 1); mbar_init(&sm.aln_full, M_WORKERS);
+    for (int i = 0; i < 4; ++i) { mbar_init(&sm.acc1_full[i], 1); mbar_init(&sm.acc1_empty[i], M_WORKERS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.h_full[i], M_WORKERS); mbar_init(&sm.h_free[i], 1); }
     mbar_init(&sm.acc0_final, 1); mbar_init(&sm.acc0_empty, M_EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -154,7 +204,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
   const uint32_t tmem = sm.tmem_base;
 
   if (warp < 8) {
-    // =============================================== producers (phase 1) ===============================================
+    // =============================================== producers (phase 1) + GELU workers 0, 1 ===============================================
     const int a_row = (warp & 3) * 32 + lane, a_c0 = (warp >> 2) * 4;
     const uint32_t a_lane = ((uint32_t)((warp & 3) * 32)) << 16;
     const int f_c = tid & 7, f_r = tid >> 3;
@@ -213,78 +263,73 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
             lo[cc * 4 + j] = __float_as_uint(vv[j] - h);
           }
         }
-        // A buffer pu & 1 (TMEM columns of the fc1 accumulators): free once the MMAs of the phase-1 unit two back are
-        // complete; for the first two units of a tile, once ALL MMAs of the previous tile are (acc0_final)
-        if (kb >= 2) {
-          const uint32_t g = (uint32_t)it * upt + kb - 2;
+        // A buffer kb % 4 (TMEM columns of the fc1 accumulators and of LN2(x1), both idle in phase 1): free once the MMAs of the
+        // phase-1 unit four back are complete.  The producers wait for the unit THREE back: the `done` barriers rotate with
+        // the three weight slots, and a wait further back could miss its phase (the barrier would already be two ahead).
+        // At the start of a tile: once ALL MMAs of the previous tile are complete (acc0_final)
+        if (kb >= M_NB) {
+          const uint32_t g = (uint32_t)it * upt + kb - M_NB;
           mbar_wait_warp(&sm.done[g % M_NB], (g / M_NB) & 1);
-        } else if (it > 0) {
-          mbar_wait_warp(&sm.acc0_final, (it - 1) & 1, (dbg & 2) ? 512 : 0);
+        } else if (it > 0 && kb == 0) {
+          mbar_wait_warp(&sm.acc0_final, (it - 1) & 1);
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ta = tmem + a_lane + (uint32_t)(M_COL_X + (pu & 1) * 64 + a_c0 * 4);
+        const uint32_t ta = tmem + a_lane + abuf_col(kb % M_ABUF) + (uint32_t)(a_c0 * 4);
         tmem_st16(ta, hi);
         tmem_st16(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
       }
-      // phase 3: the producers are GELU workers 0 and 1 of their lane quarter
+      // LayerNorm and phase 3: the producers are workers 0 and 1 of their lane quarter
+      mbar_wait_warp(&sm.p1_full, it & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      ln_worker(sm, tmem + a_lane, warp & 3, a_row, warp >> 2, lane);
       for (int c = 0; c < M_NCH; ++c)
         gelu_worker(sm, tmem + a_lane, sH, a_row, warp >> 2, (uint32_t)(it * M_NCH + c),
-                    sm.b1 + ((c + rot) & 7) * M_CH + (warp >> 2) * 16, lane, nullptr);
+                    sm.b1 + ((c + rot) & (M_NCH - 1)) * M_CH + (warp >> 2) * 8, lane, nullptr);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-  } else if (warp == M_MMA_WARP) {
-    // =============================================== MMA issuer ===============================================
-    const uint32_t idesc128 = idesc_n(128), idesc64 = idesc_n(64);
+  } else if (warp == M_MMA_WARP || warp == M_MMA2_WARP) {
+    // =============================================== MMA issuers ===============================================
+    const uint32_t idesc128 = idesc_n(128), idesc32 = idesc_n(32);
     const uint32_t acc0 = tmem;
-    const uint64_t dHh0 = make_desc(smem_u32(sH)), dHl0 = make_desc(smem_u32(sH + 2 * M_TILE));
     uint32_t g = 0;           // global unit counter (weight ring)
     uint32_t pu = 0;          // phase-1 unit counter (A buffers / hand-off barriers)
-    uint32_t gc = 0;          // global hidden-chunk counter
-    auto wait_all = [&](uint64_t* bar, uint32_t parity) {
-      if (dbg & 4096) { const uint32_t addr = smem_u32(bar); while (!mbar_try(addr, parity)) {} } else mbar_wait_warp(bar, parity);
-    };
-    auto wait_b = [&](uint32_t unit) { wait_all(&sm.full_b[unit % M_NB], (unit / M_NB) & 1); };
-    // one F1 unit: 8 k-steps of the k-block pair p against 64 fc1 rows; A = LN2(x1) from TMEM
-    auto issue_f1 = [&](uint32_t c_local, uint32_t cg, int p) {
+    uint32_t gc = 0;          // global hidden-chunk counter of the tile's first chunk
+    auto wait_b = [&](uint32_t unit) { mbar_wait_warp(&sm.full_b[unit % M_NB], (unit / M_NB) & 1); };
+    // F1 unit: fc1 rows of one hidden chunk (N = 32) over the whole K = 128; A = LN2(x1) from TMEM
+    auto issue_f1 = [&](uint32_t cg) {
+      if (cg >= 4) {                                                       // accumulator cg & 3 drained (chunk cg - 4)
+        mbar_wait_warp(&sm.acc1_empty[cg & 3], ((cg >> 2) - 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
       mtrace(tp, g * 4 + 0);
-      if (dbg & 512) {          // fine-grained stamps (debug): 1024 + g*8 + {0 start, 1 after try_wait, 2 after syncwarp, 3 in elected block}
-        mtrace(tp, 1024 + g * 8 + 0);
-        if (lane == 0) { mbar_wait(&sm.full_b[g % M_NB], (g / M_NB) & 1); mtrace(tp, 1024 + g * 8 + 1); }
-        __syncwarp();
-        mtrace(tp, 1024 + g * 8 + 2);
-      } else
       wait_b(g);
       mtrace(tp, g * 4 + 1);
       if (elect_one()) {
-        if (dbg & 512) mtrace(tp, 1024 + g * 8 + 3);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (dbg & 512) mtrace(tp, 1024 + g * 8 + 4);
         const uint32_t bslot = smem_u32(sW(g % M_NB));
-        const uint32_t d = tmem + (uint32_t)(M_COL_X + (cg & 1) * 64);
+        const uint32_t d = tmem + (uint32_t)(M_COL_X + (cg & 3) * M_CH);
 #pragma unroll
-        for (int kk = 0; kk < ((dbg & 8) ? 0 : 8); ++kk) {
-          const uint64_t dBh = make_desc(bslot + (kk >> 2) * (M_TILE / 2)) + (uint64_t)((kk & 3) * 2);
-          const uint64_t dBl = make_desc(bslot + M_TILE + (kk >> 2) * (M_TILE / 2)) + (uint64_t)((kk & 3) * 2);
-          const uint32_t kcol = (uint32_t)(p * 64 + kk * 8);
-          umma_tf32_ta(d, tmem + M_COL_ALN_LO + kcol, dBh, idesc64, (p > 0 || kk > 0) ? 1u : 0u);
-          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kcol, dBl, idesc64, 1u);
-          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kcol, dBh, idesc64, 1u);
+        for (int kk = 0; kk < 16; ++kk) {
+          // k-block kk / 4: a [32 n x 32 k] sub-image (4 KB) of the unit's hi / lo image; 32-byte step kk % 4 inside its rows
+          const uint64_t dBh = make_desc(bslot + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2);
+          const uint64_t dBl = make_desc(bslot + M_TILE + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2);
+          umma_tf32_ta(d, tmem + M_COL_ALN_LO + kk * 8, dBh, idesc32, kk > 0 ? 1u : 0u);
+          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kk * 8, dBl, idesc32, 1u);
+          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kk * 8, dBh, idesc32, 1u);
         }
-        if (dbg & 512) mtrace(tp, 1024 + g * 8 + 5);
         umma_commit(&sm.done[g % M_NB]);
-        if (p == 1) umma_commit(&sm.acc1_full[cg & 1]);
-        if (dbg & 512) mtrace(tp, 1024 + g * 8 + 6);
+        umma_commit(&sm.acc1_full[cg & 3]);
       }
       __syncwarp();
       mtrace(tp, g * 4 + 2);
       ++g;
-      (void)c_local;
     };
-    // one F2 unit: 4 k-steps of hidden k-block q against the 128 fc2 rows; A = GELU'd hidden chunk from shared memory
-    auto issue_f2 = [&](int q, bool last_of_chunk, bool last_of_tile) {
+    // F2 unit: the 128 fc2 rows against one hidden chunk (K = 32); A = GELU'd hidden chunk from shared memory
+    auto issue_f2 = [&](uint32_t cg, bool last_of_tile) {
+      mbar_wait_warp(&sm.h_full[cg & 1], (cg >> 1) & 1);
       mtrace(tp, g * 4 + 0);
       wait_b(g);
       mtrace(tp, g * 4 + 1);
@@ -292,71 +337,74 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t bslot = smem_u32(sW(g % M_NB));
         const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + M_TILE);
-        const uint64_t dAh = dHh0 + (uint64_t)(q * (M_TILE >> 4)), dAl = dHl0 + (uint64_t)(q * (M_TILE >> 4));
+        const uint32_t hbuf = smem_u32(sH + (cg & 1) * M_UNIT);
+        const uint64_t dAh = make_desc(hbuf), dAl = make_desc(hbuf + M_TILE);
 #pragma unroll
-        for (int ks = 0; ks < ((dbg & 4) ? 0 : 4); ++ks) {
+        for (int ks = 0; ks < 4; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 2);
           umma_tf32(acc0, dAl + adv, dBh + adv, idesc128, 1u);
           umma_tf32(acc0, dAh + adv, dBl + adv, idesc128, 1u);
           umma_tf32(acc0, dAh + adv, dBh + adv, idesc128, 1u);
         }
         umma_commit(&sm.done[g % M_NB]);
-        if (last_of_chunk) umma_commit(&sm.h_free);
+        umma_commit(&sm.h_free[cg & 1]);
         if (last_of_tile) umma_commit(&sm.acc0_final);
       }
       __syncwarp();
       mtrace(tp, g * 4 + 2);
       ++g;
     };
+    // position of a phase-3 unit in the tile's stream: F1(c) and F2(c) interleave as F1(0) F1(1) F1(2) [F1(c+3) F2(c)] ... F2(13..15)
+    auto pos_f1 = [&](int c) { return n1 + (c < M_AHEAD ? c : M_AHEAD + 2 * (c - M_AHEAD)); };
+    auto pos_f2 = [&](int c) { return n1 + (c <= M_NCH - 1 - M_AHEAD ? M_AHEAD + 2 * c + 1 : c + M_NCH); };
     int it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
-      if (it > 0) wait_all(&sm.acc0_empty, (it - 1) & 1);          // previous tile's x has been read out of acc0
-      // ---- phase 1: acc0 = [att | x] . [Wproj | I]^T
-      for (int kb = 0; kb < n1; ++kb, ++pu, ++g) {
-        mtrace(tp, g * 4 + 0);
-        asm volatile("bar.sync %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
-        mtrace(tp, g * 4 + 3);
-        wait_b(g);
-        mtrace(tp, g * 4 + 1);
-        if (elect_one()) {
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t bslot = smem_u32(sW(g % M_NB));
-          const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + M_TILE);
-          const uint32_t tAh = tmem + (uint32_t)(M_COL_X + (pu & 1) * 64), tAl = tAh + 32;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);
-            umma_tf32_ta(acc0, tAl + ks * 8, dBh + adv, idesc128, (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
-            umma_tf32_ta(acc0, tAh + ks * 8, dBh + adv, idesc128, 1u);
-          }
-          umma_commit(&sm.done[g % M_NB]);
-          if (kb == n1 - 1) umma_commit(&sm.p1_full);
-        }
-        __syncwarp();
-        mtrace(tp, g * 4 + 2);
-      }
-      // ---- phase 3: F1(0) F1(1) F2(0) F1(2) F2(1) ... F1(7) F2(6) F2(7)
-      wait_all(&sm.aln_full, it & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      for (int c = 0; c <= M_NCH; ++c) {
-        if (c < M_NCH) {
-          const uint32_t cg = gc + c;                                    // use index of accumulator cg & 1 is cg >> 1
-          if (cg >= 2) {
-            wait_all(&sm.acc1_empty[cg & 1], ((cg >> 1) - 1) & 1);
+    if (warp == M_MMA_WARP) {
+      for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
+        if (it > 0) mbar_wait_warp(&sm.acc0_empty, (it - 1) & 1);         // previous tile's x has been read out of acc0
+        // ---- phase 1: acc0 = [att | x] . [Wproj | I]^T
+        g = (uint32_t)it * upt;
+        for (int kb = 0; kb < n1; ++kb, ++pu, ++g) {
+          mtrace(tp, g * 4 + 0);
+          asm volatile("bar.sync %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
+          mtrace(tp, g * 4 + 3);
+          wait_b(g);
+          mtrace(tp, g * 4 + 1);
+          if (elect_one()) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t bslot = smem_u32(sW(g % M_NB));
+            const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + M_TILE);
+            const uint32_t tAh = tmem + abuf_col(kb % M_ABUF), tAl = tAh + 32;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 2);
+              umma_tf32_ta(acc0, tAl + ks * 8, dBh + adv, idesc128, (kb > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
+              umma_tf32_ta(acc0, tAh + ks * 8, dBh + adv, idesc128, 1u);
+            }
+            umma_commit(&sm.done[g % M_NB]);
+            if (kb == n1 - 1) umma_commit(&sm.p1_full);
           }
-          issue_f1(c, cg, 0);
-          issue_f1(c, cg, 1);
+          __syncwarp();
+          mtrace(tp, g * 4 + 2);
         }
-        if (c >= 1) {
-          const uint32_t cg = gc + c - 1;
-          wait_all(&sm.h_full, cg & 1);
-          issue_f2(0, false, false);
-          issue_f2(1, true, c == M_NCH);
+        // ---- phase 3, fc2 half: F2(0..15), each as soon as its hidden chunk is in shared memory
+        for (int c = 0; c < M_NCH; ++c) {
+          g = (uint32_t)it * upt + pos_f2(c);
+          issue_f2(gc + c, c == M_NCH - 1);
         }
+        gc += M_NCH;
       }
-      gc += M_NCH;
+    } else {
+      // ---- phase 3, fc1 half (warp 18): F1(0..15), up to four accumulators ahead of the GELU workers
+      for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
+        mbar_wait_warp(&sm.aln_full, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int c = 0; c < M_NCH; ++c) {
+          g = (uint32_t)it * upt + pos_f1(c);
+          issue_f1(gc + c);
+        }
+        gc += M_NCH;
+      }
     }
   } else if (warp == M_TMA_WARP) {
     // =============================================== weight stream (TMA) ===============================================
@@ -367,25 +415,23 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
           const int slot = g % M_NB;
           if (g >= M_NB) mbar_wait(&sm.done[slot], ((g - M_NB) / M_NB) & 1);
           const uint32_t bar = smem_u32(&sm.full_b[slot]);
-          if ((dbg & 256) && g >= M_NB) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); continue; }
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(M_UNIT) : "memory");
-          // source unit: stream layout is P1(0..n1-1), F1(c,p) at n1 + 2c + p, F2(c,q) at n1 + 16 + 2c + q; issue order of
-          // phase 3 in blocks of two units: F1(0) F1(1) F2(0) F1(2) F2(1) ... F1(7) F2(6) F2(7), chunk = (c + rot) % 8
+          // source unit: the stream is laid out P1(0..n1-1) | F1(0..15) | F2(0..15); issue order of phase 3 as above, with the
+          // chunk index rotated by `rot`
           int su;
           if (u < n1) {
             su = (u + rot) % n1;
           } else {
-            const int s3 = u - n1, blk = s3 >> 1, pq = s3 & 1;
-            const bool is_f2 = blk >= 2 && (blk == 15 || (blk & 1) == 0);
-            const int cs = is_f2 ? (blk == 15 ? 7 : blk / 2 - 1) : (blk == 0 ? 0 : (blk + 1) / 2);
-            su = n1 + (is_f2 ? 16 : 0) + ((cs + rot) & 7) * 2 + pq;
+            const int s3 = u - n1;
+            int cs;
+            bool is_f2;
+            if (s3 < M_AHEAD) { is_f2 = false; cs = s3; }
+            else if (s3 < M_AHEAD + 2 * (M_NCH - M_AHEAD)) { const int j = s3 - M_AHEAD; is_f2 = j & 1; cs = is_f2 ? (j >> 1) : (j >> 1) + M_AHEAD; }
+            else { is_f2 = true; cs = s3 - M_NCH; }
+            su = n1 + (is_f2 ? M_NCH : 0) + ((cs + rot) & (M_NCH - 1));
           }
-          // several smaller bulk copies per unit: one copy keeps only a few L2 requests in flight
-          const int nsplit = (dbg & 32) ? 1 : (dbg & 64) ? 2 : (dbg & 128) ? 16 : 8;
-          const uint32_t piece = M_UNIT / nsplit;
-          for (int i = 0; i < nsplit; ++i)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(smem_u32(sW(slot)) + i * piece), "l"(a.Wstream + (size_t)su * (M_UNIT / 4) + (size_t)i * (piece / 4)), "r"(piece), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(sW(slot))), "l"(a.Wstream + (size_t)su * (M_UNIT / 4)), "r"(M_UNIT), "r"(bar) : "memory");
         }
       }
     }
@@ -393,64 +439,27 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
     // =============================================== LN / GELU / store warps ===============================================
     const int e = warp - M_EPI_WARP0;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int half = e >> 2;                   // two warps per quarter: columns [64 half, 64 half + 64) / hidden k-block `half`
+    const int half = e >> 2;                   // two warps per quarter: columns [64 half, 64 half + 64); GELU worker 2 + half
     const int row = q * 32 + lane;             // row of the tile owned by this thread
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
-    // this warp's 4 KB of the hidden buffer: rows q*32..+32 of hi image `half`; also its store staging
-    uint8_t* my_h_hi = sH + half * M_TILE;
-    uint8_t* my_h_lo = sH + (2 + half) * M_TILE;
-    float* stage = reinterpret_cast<float*>(my_h_hi + q * 32 * 128);
+    // store staging of the final epilogue: rows q*32..+32 of hidden buffer `half`'s hi image (4 KB); nobody writes the hidden
+    // buffers between the last fc2 of a tile and the LayerNorm of the next, which all eight of these warps must have passed
+    uint8_t* stage = sH + half * M_UNIT + q * 32 * 128;
     const int srow = lane >> 3, sc8 = lane & 7;
     uint32_t gc = 0;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
       const int row0 = t * M_BM;
-      // ---- LN2 of x1 = acc0 + b_proj, thread = row, two-pass (like torch); this warp normalises columns 64 half..+64 ----
+      // ---- LN2 of x1 = acc0 + b_proj: worker 2 + half of the quarter ----
       mbar_wait_warp(&sm.p1_full, it & 1);
       mtrace(tp, 3968 + it * 8 + 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float v[32];
-      float s = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        tmem_ld32(tmem + t_lane + (uint32_t)(ch * 32), v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s += v[j] + sm.bmid[ch * 32 + j];
-      }
-      const float mean = s * (1.f / 128.f);
-      float qq = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < 4; ++ch) {
-        tmem_ld32(tmem + t_lane + (uint32_t)(ch * 32), v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { const float d = (v[j] + sm.bmid[ch * 32 + j]) - mean; qq = fmaf(d, d, qq); }
-      }
-      const float rstd = 1.f / sqrtf(qq * (1.f / 128.f) + 1e-5f);
-#pragma unroll 1
-      for (int ch = 2 * half; ch < 2 * half + 2; ++ch) {
-        tmem_ld32(tmem + t_lane + (uint32_t)(ch * 32), v);
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int k = ch * 32 + j;
-          const float y = ((v[j] + sm.bmid[k]) - mean) * rstd * sm.gamma[k] + sm.beta[k];
-          const float h = rna_tf32_fast(y);
-          hi[j] = __float_as_uint(h);
-          lo[j] = __float_as_uint(y - h);
-        }
-        tmem_st16(tmem + t_lane + (uint32_t)(M_COL_ALN_HI + ch * 32), hi);
-        tmem_st16(tmem + t_lane + (uint32_t)(M_COL_ALN_HI + ch * 32 + 16), hi + 16);
-        tmem_st16(tmem + t_lane + (uint32_t)(M_COL_ALN_LO + ch * 32), lo);
-        tmem_st16(tmem + t_lane + (uint32_t)(M_COL_ALN_LO + ch * 32 + 16), lo + 16);
-      }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_m(&sm.aln_full);
+      ln_worker(sm, tmem + t_lane, q, row, 2 + half, lane);
       mtrace(tp, 3968 + it * 8 + 1);
-      // ---- hidden chunks: GELU(fc1 + b1) -> hi/lo -> shared memory (A operand of fc2); workers 2 and 3 of the quarter ----
+      float v[32];
+      // ---- hidden chunks: GELU workers 2 and 3 of the quarter ----
       for (int c = 0; c < M_NCH; ++c, ++gc)
-        gelu_worker(sm, tmem + t_lane, sH, row, 2 + half, gc, sm.b1 + ((c + rot) & 7) * M_CH + (2 + half) * 16, lane, tp);
+        gelu_worker(sm, tmem + t_lane, sH, row, 2 + half, gc, sm.b1 + ((c + rot) & (M_NCH - 1)) * M_CH + (2 + half) * 8, lane, tp);
       // ---- final: x = acc0 + (b_proj + b_fc2), columns 64 half..+64 of this warp's 32 rows, coalesced through the staging ----
       mbar_wait_warp(&sm.acc0_final, it & 1);
       mtrace(tp, 3968 + it * 8 + 2);
@@ -466,8 +475,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
         const float* src = ch == 0 ? v : w;
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8)
-          *reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(stage) + swz(lane, c8)) =
-              make_float4(src[c8 * 4], src[c8 * 4 + 1], src[c8 * 4 + 2], src[c8 * 4 + 3]);
+          *reinterpret_cast<float4*>(stage + swz(lane, c8)) = make_float4(src[c8 * 4], src[c8 * 4 + 1], src[c8 * 4 + 2], src[c8 * 4 + 3]);
         __syncwarp();
         const int n = half * 64 + ch * 32 + sc8 * 4;
         const float4 bo = *reinterpret_cast<const float4*>(sm.bout + n);
@@ -476,7 +484,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles, int dbg) {
           const int lr = i8 * 4 + srow;
           const int r = row0 + q * 32 + lr;
           if (r < a.rows) {
-            float4 o = *reinterpret_cast<const float4*>(reinterpret_cast<uint8_t*>(stage) + swz(lr, sc8));
+            float4 o = *reinterpret_cast<const float4*>(stage + swz(lr, sc8));
             o.x += bo.x; o.y += bo.y; o.z += bo.z; o.w += bo.w;
             *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
           }
@@ -514,8 +522,7 @@ int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream) {
   }
   const int ntiles = (a.rows + M_BM - 1) / M_BM;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
-  static const int dbg = [] { const char* e = getenv("NMRF_B200_DBG"); return e ? atoi(e) : 0; }();
-  mlp_chain_kernel<<<grid, M_BLOCK, M_DYN, stream>>>(a, ntiles, dbg);
+  mlp_chain_kernel<<<grid, M_BLOCK, M_DYN, stream>>>(a, ntiles);
   count_launch();
   return check_launch("mlp_chain");
 }

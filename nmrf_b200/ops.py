@@ -90,16 +90,17 @@ def _tile_images(T):
 
 
 def pack_mlp_stream(W1cat, Wfc1, Wfc2):
-    """Weight stream of nmrf_mlp_chain (P1 units, then F1(c,p), then F2(c,q); see nmrf_b200.h): W1cat [128, K1] (K1 % 32 == 0; for a block tail
+    """Weight stream of nmrf_mlp_chain (P1 units, then F1(0..15), then F2(0..15); see nmrf_b200.h): W1cat [128, K1] (K1 % 32 == 0; for a block tail
     [Wproj | I]), Wfc1 [512,128], Wfc2 [128,512] -> [K1/32 + 32, 8192] fp32."""
     for n, t in (("W1cat", W1cat), ("Wfc1", Wfc1), ("Wfc2", Wfc2)):
         _chk(t, n)
     assert W1cat.shape[0] == 128 and W1cat.shape[1] % 32 == 0 and Wfc1.shape == (512, 128) and Wfc2.shape == (128, 512)
     p1 = [W1cat[:, 32 * j:32 * j + 32] for j in range(W1cat.shape[1] // 32)]
-    f1 = lambda c: [torch.cat([Wfc1[64 * c:64 * c + 64, 64 * p:64 * p + 32], Wfc1[64 * c:64 * c + 64, 64 * p + 32:64 * p + 64]], 0)
-                    for p in range(2)]
-    f2 = lambda c: [Wfc2[:, 64 * c + 32 * q:64 * c + 32 * q + 32] for q in range(2)]
-    units = p1 + [u for c in range(8) for u in f1(c)] + [u for c in range(8) for u in f2(c)]
+    # F1(c): fc1 rows 32c..32c+31 against the whole K = 128, as four [32 n x 32 k] sub-images stacked along the rows
+    f1 = [torch.cat([Wfc1[32 * c:32 * c + 32, 32 * kb:32 * kb + 32] for kb in range(4)], 0) for c in range(16)]
+    # F2(c): the 128 fc2 rows against hidden columns 32c..32c+31
+    f2 = [Wfc2[:, 32 * c:32 * c + 32] for c in range(16)]
+    units = p1 + f1 + f2
     return _tile_images(torch.stack(units, 0))
 
 

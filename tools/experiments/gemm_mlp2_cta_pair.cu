@@ -1,3 +1,5 @@
+// EXPERIMENT, not built into libnmrf_b200.so: CTA-pair schedule of the block tail for the 64-wide-chunk weight stream of commit
+// 0c94aff..; passed tests/test_gpu_stages.py::test_mlp_chain on B200 but ran 87 us against 78 us for the single-CTA kernel.
 // nmrf_mlp_chain on CTA PAIRS (tcgen05 cta_group::2): the same fused block tail as gemm_mlp.cu
 //     x1 = [att | x] . [Wproj | I]^T + b_proj ;  x = x1 + fc2(GELU(fc1(LN2(x1))))        (NMP.py:358-363, 570-573)
 // but two CTAs of a cluster take a 256-token tile together.  Each CTA owns 128 rows (its A operands, accumulators, LayerNorm,

@@ -7,9 +7,9 @@
 // TMEM (tcgen05.st) and the UMMA takes A from TMEM: shared memory carries the weight tiles (B) and the raw A ring.
 //
 //   warps 0-7   producers   thread = (row, half of the 32-wide k-block): warp w owns TMEM lane quarter w%4 and k-columns
-//                           16*(w/4)..+16.  The raw A tile [128 x 32] of a k-block comes into a 4-deep swizzled smem ring by
+//                           16*(w/4)..+16.  The raw A tile [128 x 32] of a k-block comes into a 3-deep swizzled smem ring by
 //                           COALESCED cp.async (8 lanes = one row's 128 B; a per-thread row gather costs 32 L1 wavefronts
-//                           per instruction); the ring streams ACROSS tiles, three k-blocks ahead.  Per k-block: LDS ->
+//                           per instruction); the ring streams ACROSS tiles, two k-blocks ahead.  Per k-block: LDS ->
 //                           LayerNorm -> hi/lo split in registers, THEN wait for the MMAs that still read the A buffer,
 //                           then tcgen05.st (A_hi / A_lo -> TMEM) and hand over to the MMA warp.
 //   warp  8     MMA issuer  per unit: 4 k-steps x {A_lo.B_hi, A_hi.B_lo, A_hi.B_hi}, A from TMEM, B from swizzled smem
@@ -17,7 +17,8 @@
 //                           wait they also compute the LayerNorm statistics of the tile three ahead (the producers used
 //                           to stall ~10k cycles per tile on those loads)
 //   warp  17    TMA         one lane streams the pre-swizzled weight tile images (2 x 16 KB cp.async.bulk per unit) into a
-//                           3-slot ring, as soon as the MMAs that read a slot have completed
+//                           4-slot ring, as soon as the MMAs that read a slot have completed (a fourth slot instead of a
+//                           fourth raw-A stage: the MMA warp waited ~300 cycles per unit for weights with three)
 //
 //   tile        128 rows x 128 output columns, unit = one k-block of 32; three accumulator stages (3 x 128 TMEM columns)
 //               so the epilogue of a tile overlaps the MMAs of the next two; A tiles double buffered (2 x 64 columns).
@@ -31,7 +32,7 @@ namespace nmrf {
 namespace {
 using namespace tc;
 
-constexpr int G6_BM = 128, G6_BN = 128, G6_BK = 32, G6_NB = 3, G6_ACC = 3;
+constexpr int G6_BM = 128, G6_BN = 128, G6_BK = 32, G6_NB = 4, G6_ACC = 3;
 constexpr int G6_ACOL = G6_ACC * G6_BN;             // first TMEM column of the A buffers
 constexpr int G6_TILE = G6_BM * G6_BK * 4;          // 16 KB operand tile
 constexpr int G6_PROD = 256;                        // producer threads (warps 0-7)
@@ -42,9 +43,9 @@ constexpr int G6_BLOCK = (G6_TMA_WARP + 1) * 32;               // 576
 constexpr int G6_HANDOFF = G6_PROD + 32;            // named barriers 1..3: producers arrive, MMA warp syncs
 constexpr int G6_RAW_BAR = 5;                       // named barrier of the producers: raw tile visible / consumed
 constexpr int G6_STAGE_FLOATS = 32 * 36;            // per-epilogue-warp transpose tile
-constexpr int G6_RAW = 4;                           // raw-A ring depth (k-blocks)
+constexpr int G6_RAW = 3;                           // raw-A ring depth (k-blocks)
 constexpr int G6_STATS = 4;                         // LayerNorm statistics buffers (tiles in flight: 3 ahead)
-constexpr int G6_DYN = (6 + G6_RAW) * G6_TILE + G6_EPI_WARPS * G6_STAGE_FLOATS * 4 + 1024;   // B_hi[3] B_lo[3] raw[4] + epilogue staging
+constexpr int G6_DYN = (2 * G6_NB + G6_RAW) * G6_TILE + G6_EPI_WARPS * G6_STAGE_FLOATS * 4 + 1024;   // B_hi[4] B_lo[4] raw[3] + epilogue staging
 
 struct G6Smem {
   uint64_t done[G6_NB];       // MMAs of the unit that used B slot s are complete (tcgen05.commit)
@@ -111,9 +112,9 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
   __shared__ G6Smem sm;
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
   auto sB_hi = [&](int i) { return base + i * G6_TILE; };
-  auto sB_lo = [&](int i) { return base + (3 + i) * G6_TILE; };
-  auto sRaw = [&](int i) { return base + (6 + i) * G6_TILE; };
-  float* stage_base = reinterpret_cast<float*>(base + (6 + G6_RAW) * G6_TILE);
+  auto sB_lo = [&](int i) { return base + (G6_NB + i) * G6_TILE; };
+  auto sRaw = [&](int i) { return base + (2 * G6_NB + i) * G6_TILE; };
+  float* stage_base = reinterpret_cast<float*>(base + (2 * G6_NB + G6_RAW) * G6_TILE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long* const tp = (blockIdx.x == 0 && (tid == 0 || tid == G6_MMA_WARP * 32 || tid == G6_EPI_WARP0 * 32)) ? g_trace6 : nullptr;
@@ -182,7 +183,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch_next(0); fetch_next(1); fetch_next(2);
+    fetch_next(0); fetch_next(1);
     uint32_t unit = 0;         // == k-blocks produced so far by this CTA: ring stage unit % 4, A buffer unit & 1, B slot unit % 3
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
@@ -197,8 +198,10 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
         const int slot = unit % G6_NB;
         trace(tp, unit * 8 + 0);
         // this k-block's raw tile has landed for every producer thread (own copies: wait_group; others': barrier)
-        asm volatile("cp.async.wait_group 2;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(G6_RAW_BAR), "r"(G6_PROD) : "memory");
+        // the stage consumed one unit ago is free again (every producer is past its reads): re-arm it two k-blocks ahead
+        fetch_next((unit + 2) % G6_RAW);
         trace(tp2, 1024 + unit * 8 + 0);
         const uint8_t* raw = sRaw(unit % G6_RAW);
         uint32_t hi[16], lo[16];
@@ -238,9 +241,6 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");
         trace(tp, unit * 8 + 2);
         trace(tp2, 1024 + unit * 8 + 4);
-        // re-arm the ring three k-blocks ahead: that stage was consumed (by every producer) one unit ago, before the
-        // barrier above
-        fetch_next((unit + 3) % G6_RAW);
         trace(tp2, 1024 + unit * 8 + 5);
       }
     }

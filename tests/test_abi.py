@@ -20,7 +20,7 @@ def _declared():
 def test_header_symbols_are_exported():
     from nmrf_b200 import _lib
     decl = _declared()
-    assert len(decl) >= 16
+    assert len(decl) >= 26
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in decl:
         assert hasattr(lib, name), f"{name} declared in include/nmrf_b200.h but not exported"

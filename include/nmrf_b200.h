@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NMRF_B200_ABI_VERSION 5
+#define NMRF_B200_ABI_VERSION 6
 
 enum {
   NMRF_OK = 0,
@@ -96,6 +96,7 @@ typedef struct {
   const float* bias_out;                       /* [128] */
   float* Y; int ldy;
   int rows;
+  int e_identity;                              /* 1: the E columns of W1cat are the identity (residual): their zero lo image is skipped */
 } nmrf_mlp_args;
 int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream);
 

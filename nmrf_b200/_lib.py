@@ -9,7 +9,7 @@ from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class GemmArgs(Structure):
@@ -40,7 +40,7 @@ class MlpArgs(Structure):
         ("b1", c_void_p),
         ("bias_out", c_void_p),
         ("Y", c_void_p), ("ldy", c_int),
-        ("rows", c_int),
+        ("rows", c_int), ("e_identity", c_int),
     ]
 
 

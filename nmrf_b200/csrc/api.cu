@@ -61,7 +61,7 @@ int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const f
 
 using namespace nmrf;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
-static_assert(sizeof(nmrf_gemm_args) == 144 && sizeof(nmrf_mlp_args) == 96, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
+static_assert(sizeof(nmrf_gemm_args) == 144 && sizeof(nmrf_mlp_args) == 104, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
 
 // NMRF_B200_ATTN=simt selects the fp32-FMA attention kernels (default: tcgen05 3xTF32)
 static std::atomic<int> g_attn_tc{-1};

@@ -374,11 +374,13 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
             const uint32_t bslot = smem_u32(sW(g % M_NB));
             const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + M_TILE);
             const uint32_t tAh = tmem + abuf_col(kb % M_ABUF), tAl = tAh + 32;
+            // k-blocks of E meet the identity block of the weight, whose lo image is all zero: its A_hi . B_lo product is skipped
+            const bool lo_is_zero = a.e_identity && ((kb + rot) % n1) * M_BK >= a.Kx;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
               umma_tf32_ta(acc0, tAl + ks * 8, dBh + adv, idesc128, (kb > 0 || ks > 0) ? 1u : 0u);
-              umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
+              if (!lo_is_zero) umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
               umma_tf32_ta(acc0, tAh + ks * 8, dBh + adv, idesc128, 1u);
             }
             umma_commit(&sm.done[g % M_NB]);

@@ -204,7 +204,7 @@ class _Launches:
         a.E, a.lde, a.Ke = x.data_ptr(), x.stride(0), 128
         a.Wstream, a.bias_mid, a.ln_gamma, a.ln_beta = ws.data_ptr(), proj_b.data_ptr(), n2[0].data_ptr(), n2[1].data_ptr()
         a.b1, a.bias_out = fc1_b.data_ptr(), bias_out.data_ptr()
-        a.Y, a.ldy, a.rows = x.data_ptr(), x.stride(0), rows
+        a.Y, a.ldy, a.rows, a.e_identity = x.data_ptr(), x.stride(0), rows, 1
         self.keep(a, att, x, ws, bias_out, proj_b, n2, fc1_b)
         flops = 2.0 * rows * (128 * 128 + 2 * 128 * 512)
         self.add(lib.nmrf_mlp_chain, what, ctypes.byref(a), flops=flops, bytes=4.0 * rows * 128 * 3)

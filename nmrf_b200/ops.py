@@ -104,7 +104,7 @@ def pack_mlp_stream(W1cat, Wfc1, Wfc2):
     return _tile_images(torch.stack(units, 0))
 
 
-def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None):
+def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_identity=False):
     """Y = x1 + fc2(GELU(fc1(LN(x1)))) + b_fc2 with x1 = concat(X, E) @ W1cat.T + bias_mid (bias_out = bias_mid + b_fc2);
     wstream from pack_mlp_stream.  `out` may alias E."""
     for n, t in (("X", X), ("E", E), ("wstream", wstream), ("bias_mid", bias_mid), ("gamma", ln[0]), ("beta", ln[1]), ("b1", b1),
@@ -120,7 +120,7 @@ def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None):
     a.E, a.lde, a.Ke = _p(E), (E.stride(0) if E is not None else 0), Ke
     a.Wstream, a.bias_mid, a.ln_gamma, a.ln_beta = wstream.data_ptr(), bias_mid.data_ptr(), ln[0].data_ptr(), ln[1].data_ptr()
     a.b1, a.bias_out = b1.data_ptr(), bias_out.data_ptr()
-    a.Y, a.ldy, a.rows = Y.data_ptr(), Y.stride(0), rows
+    a.Y, a.ldy, a.rows, a.e_identity = Y.data_ptr(), Y.stride(0), rows, int(e_identity)
     _lib.check(lib.nmrf_mlp_chain(ctypes.byref(a), _stream()), "mlp_chain")
     return Y
 

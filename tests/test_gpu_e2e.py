@@ -73,6 +73,7 @@ def test_against_reference_golden(name):
     (1, 120, 200, 96, 3, (2, 2, 2)),      # window pads in both stacks, K=3
     (2, 136, 240, 192, 4, (2, 3, 2)),     # batch 2, odd layer count (shifted last layer)
     (1, 270, 480, 192, 4, (5, 5, 5)),     # checkpoint-compatible depth at half the benchmark size
+    (2, 375, 1248, 192, 4, (1, 1, 1)),    # KITTI geometry (BASELINE config 2): 375 -> 376 rows, 47 x 156 grid padded to 48 x 156
 ])
 def test_against_oracle(B, H, W, max_disp, K, L):
     model, sd = build_product_model(max_disp, K, L, 0, "reference")

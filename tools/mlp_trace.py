@@ -12,10 +12,10 @@ Wp, W1, W2 = (torch.randn(128, 128, generator=g) / 11).to(dev), (torch.randn(512
 ws = ops.pack_mlp_stream(torch.cat([Wp, torch.eye(128, device=dev)], 1).contiguous(), W1, W2)
 z, o, b1 = torch.zeros(128, device=dev), torch.ones(128, device=dev), torch.zeros(512, device=dev)
 for _ in range(3):
-    ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x)
+    ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x, e_identity=True)
 tr = torch.zeros(4096, dtype=torch.int64, device=dev)
 _lib.check(_lib.lib.nmrf_debug_set_trace(tr.data_ptr()), "set_trace")
-ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x)
+ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x, e_identity=True)
 torch.cuda.synchronize()
 _lib.check(_lib.lib.nmrf_debug_set_trace(None), "set_trace")
 t = tr.cpu().tolist()

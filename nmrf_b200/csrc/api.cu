@@ -30,6 +30,8 @@ int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stre
 int gemm_set_trace(long long* dev_ptr);
 int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
+int token_gemm_ws(const nmrf_gemm_args& a, cudaStream_t stream);
+bool token_gemm_ws_supported(const nmrf_gemm_args& a);
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
 int mlp_set_trace(long long* dev_ptr);
 int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream);
@@ -99,6 +101,10 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
     NMRF_REQUIRE(a->ldw % 32 == 0 && a->ldw >= kpad, "token_gemm(tc): ldw=%d must be a multiple of 32 and >= %d", a->ldw, kpad);
     // NMRF_B200_GEMM_V selects an older schedule of the same arithmetic (4: single-role, 5: A operand in shared memory)
     static const int ver = [] { const char* e = getenv("NMRF_B200_GEMM_V"); return (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 6; }();
+    // experiment (NMRF_B200_GEMM_WS=1): K <= 192 with the weights stationary in tensor memory (gemm_ws.cu); correct, but
+    // 54 vs 44 us for the qkv projection -- weight traffic is not what bounds these GEMMs
+    static const int ws = [] { const char* e = getenv("NMRF_B200_GEMM_WS"); return (e && e[0] == '1') ? 1 : 0; }();
+    if (ws && ver == 6 && token_gemm_ws_supported(*a)) return token_gemm_ws(*a, ST(stream));
     if (ver == 4) return token_gemm_tc(*a, a->W_lo, ST(stream));
     if (ver == 5 || !a->Wt_hi || !a->Wt_lo) return token_gemm_tc5(*a, a->W_lo, ST(stream));
     return token_gemm_tc6(*a, a->W_lo, ST(stream));

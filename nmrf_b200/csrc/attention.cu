@@ -12,39 +12,50 @@ namespace {
 constexpr float kScale = 0.17677669529663687f;   // 32^-0.5 (NMP.py:79,163,412)
 
 // ------------------------------------------------------------------------------------------------
-// A10: one warp per pixel, lane = head-dim channel.
+// A10: one warp per pixel; lane = (head, 4 of its 32 channels): the four heads run side by side, every load is a float4 (a
+// warp instruction covers the 512 contiguous bytes of one of q / k / v of a token) and a q.k dot product needs three shuffle
+// stages (the earlier lane = channel mapping walked the heads one after the other with five-stage reductions: 320 dependent
+// shuffles per pixel, 2 TB/s).
 // ------------------------------------------------------------------------------------------------
 __global__ void proposal_attention_kernel(const float* __restrict__ qkv, int P, int K, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int p = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (p >= P) return;
-  const float* base = qkv + (size_t)p * K * kQkv;
-  for (int hd = 0; hd < kHeads; ++hd) {
-    float q[kMaxK], k[kMaxK], v[kMaxK];
+  const float* base = qkv + (size_t)p * K * kQkv + lane * 4;        // head lane / 8, channels 4 (lane % 8) .. + 3
+  float4 q[kMaxK], k[kMaxK], v[kMaxK];
 #pragma unroll
-    for (int i = 0; i < kMaxK; ++i) {
-      if (i < K) {
-        q[i] = base[i * kQkv + hd * 32 + lane];
-        k[i] = base[i * kQkv + 128 + hd * 32 + lane];
-        v[i] = base[i * kQkv + 256 + hd * 32 + lane];
-      } else { q[i] = k[i] = v[i] = 0.f; }
-    }
+  for (int i = 0; i < kMaxK; ++i) {
+    if (i < K) {
+      q[i] = *reinterpret_cast<const float4*>(base + i * kQkv);
+      k[i] = *reinterpret_cast<const float4*>(base + i * kQkv + 128);
+      v[i] = *reinterpret_cast<const float4*>(base + i * kQkv + 256);
+    } else { q[i] = k[i] = v[i] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  }
 #pragma unroll
-    for (int i = 0; i < kMaxK; ++i) {
-      if (i >= K) break;
-      float s[kMaxK];
-      float m = -INFINITY;
+  for (int i = 0; i < kMaxK; ++i) {
+    if (i >= K) break;
+    float s[kMaxK];
+    float m = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < kMaxK; ++j) {
-        if (j < K) { s[j] = warp_sum(q[i] * k[j]) * kScale; m = fmaxf(m, s[j]); }
+    for (int j = 0; j < kMaxK; ++j) {
+      if (j < K) {
+        float d = (q[i].x * k[j].x + q[i].y * k[j].y) + (q[i].z * k[j].z + q[i].w * k[j].w);
+        d += __shfl_xor_sync(0xffffffffu, d, 1); d += __shfl_xor_sync(0xffffffffu, d, 2); d += __shfl_xor_sync(0xffffffffu, d, 4);
+        s[j] = d * kScale;
+        m = fmaxf(m, s[j]);
       }
-      float sum = 0.f, o = 0.f;
-#pragma unroll
-      for (int j = 0; j < kMaxK; ++j) {
-        if (j < K) { const float e = expf(s[j] - m); sum += e; o = fmaf(e, v[j], o); }
-      }
-      out[((size_t)p * K + i) * kEmbed + hd * 32 + lane] = o / sum;
     }
+    float sum = 0.f;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < kMaxK; ++j) {
+      if (j < K) {
+        const float e = expf(s[j] - m);
+        sum += e;
+        o.x = fmaf(e, v[j].x, o.x); o.y = fmaf(e, v[j].y, o.y); o.z = fmaf(e, v[j].z, o.z); o.w = fmaf(e, v[j].w, o.w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + ((size_t)p * K + i) * kEmbed + lane * 4) = make_float4(o.x / sum, o.y / sum, o.z / sum, o.w / sum);
   }
 }
 

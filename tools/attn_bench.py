@@ -39,3 +39,8 @@ for impl in (0, 1):
 d = (res[0][1] - res[1][1]).abs().max().item() / res[0][1].abs().max().item()
 print(f"stripe 68x120 K=4: simt {res[0][0]:.1f} us, tcgen05 {res[1][0]:.1f} us, max rel diff {d:.2e}")
 _lib.check(_lib.lib.nmrf_set_attention_impl(1), "impl")
+
+# intra-pixel proposal attention (inference stack): 72 x 120 padded grid, K = 4
+P, K = 72 * 120, 4
+qkv = torch.randn(P * K, 384, generator=g).cuda()
+print(f"proposal attention P={P} K={K}: {timeit(lambda: ops.proposal_attention(qkv, K)):.1f} us")

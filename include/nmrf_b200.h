@@ -76,15 +76,16 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
  * hi_tiles / lo_tiles must hold ceil(N/128)*ceil(K/32)*4096 floats each. */
 int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float* lo_tiles, void* stream);
 /* ---- fused block tail: proj + residual + LayerNorm + Mlp in ONE launch ----------------------------
- *   x1 = concat(X[r, 0:Kx], E[r, 0:Ke]) . W1cat^T + bias_mid        (SwinNMP / CSWinNMP: x + proj(attn), NMP.py:358-359,
- *                                                                    570-571; the caller puts [Wproj | I] in the stream and the
- *                                                                    residual stream x in E, so the add happens in the tensor core)
+ *   x1 = X[r, 0:Kx] . W1^T + bias_mid + E[r, 0:128]                  (e_identity = 1; SwinNMP / CSWinNMP: x + proj(attn),
+ *                                                                    NMP.py:358-359, 570-571: E is the residual stream x, which is
+ *                                                                    loaded into the fp32 accumulator before the MMAs, i.e. added exactly)
+ *   x1 = concat(X[r, 0:Kx], E[r, 0:Ke]) . W1cat^T + bias_mid         (e_identity = 0: E is an ordinary concatenated operand)
  *   Y  = x1 + fc2( GELU( fc1( LN(x1) ) ) ) + b_fc2                   (x + Mlp(norm2(x)), NMP.py:362-363,572-573; timm Mlp 128->512->128)
- * Wstream: (Kx+Ke)/32 + 32 units of 8192 floats (16 KB hi image + 16 KB lo image, SWIZZLE_128B shared-memory images of
- * [128 x 32] fp32 tiles):  P1(0..n1-1), then F1(c) at n1 + c, then F2(c) at n1 + 16 + c (c = hidden chunk of 32, 0..15; every
- * CTA walks the k-blocks and the chunks starting from its own rotation, so the fp32 summation order differs per tile):
- * P1(j)[n,k] = W1cat[n, 32j+k];  F1(c)[r,k] = Wfc1[32c + r%32, 32(r/32) + k];  F2(c)[n,k] = Wfc2[n, 32c+k]
- * (nmrf_b200/hotpath.py: pack_mlp_stream).  bias_out = bias_mid + b_fc2.  Kx+Ke must be a multiple of 32 (<= 512);
+ * Wstream: n1 + 32 units of 8192 floats, n1 = Kx/32 (e_identity) or (Kx+Ke)/32 (16 KB hi image + 16 KB lo image, SWIZZLE_128B
+ * shared-memory images of [128 x 32] fp32 tiles):  P1(0..n1-1), then F1(c) at n1 + c, then F2(c) at n1 + 16 + c (c = hidden chunk
+ * of 32, 0..15; every CTA walks the k-blocks and the chunks starting from its own rotation, so the fp32 summation order differs
+ * per tile):  P1(j)[n,k] = W1[n, 32j+k];  F1(c)[r,k] = Wfc1[32c + r%32, 32(r/32) + k];  F2(c)[n,k] = Wfc2[n, 32c+k]
+ * (nmrf_b200/ops.py: pack_mlp_stream).  bias_out = bias_mid + b_fc2.  Kx and Ke must be multiples of 32, Kx + Ke <= 512;
  * Y may alias E (each tile is read completely before it is written).  Same 3xTF32 arithmetic as nmrf_token_gemm. */
 typedef struct {
   const float* X; int ldx; int Kx;
@@ -96,7 +97,7 @@ typedef struct {
   const float* bias_out;                       /* [128] */
   float* Y; int ldy;
   int rows;
-  int e_identity;                              /* 1: the E columns of W1cat are the identity (residual): their zero lo image is skipped */
+  int e_identity;                              /* 1: E [rows,128] is the residual, added exactly (not part of the weight stream) */
 } nmrf_mlp_args;
 int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream);
 

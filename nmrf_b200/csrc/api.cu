@@ -118,6 +118,7 @@ int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream) {
   NMRF_REQUIRE(a->Kx > 0 && a->Kx % 32 == 0 && a->Ke >= 0 && a->Ke % 32 == 0 && a->Kx + a->Ke <= 512,
                "mlp_chain: Kx=%d Ke=%d must be multiples of 32, sum <= 512", a->Kx, a->Ke);
   NMRF_REQUIRE((a->Ke == 0) == (a->E == nullptr), "mlp_chain: E/Ke mismatch");
+  NMRF_REQUIRE(!a->e_identity || a->Ke == 128, "mlp_chain: a residual E (e_identity) must have 128 columns, Ke=%d", a->Ke);
   NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldy % 4 == 0 && (a->Ke == 0 || a->lde % 4 == 0), "mlp_chain: bad leading dimension");
   if (a->rows == 0) return NMRF_OK;
   return mlp_chain(*a, ST(stream));

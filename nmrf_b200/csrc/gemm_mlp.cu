@@ -1,6 +1,6 @@
 // Fused message-passing tail on tcgen05: one kernel per block for everything that is row-local after the attention
-//     x1 = [att | x] . [Wproj | I]^T + b_proj          (NMP.py:358-359,570-571: proj + residual; the residual rides the
-//                                                       tensor core as an identity block of the weight)
+//     x1 = att . Wproj^T + b_proj + x                  (NMP.py:358-359,570-571: proj + residual; the residual x is PRELOADED
+//                                                       into the accumulator in full fp32 -- tcgen05.st -- before the MMAs)
 //     x  = x1 + fc2( GELU( fc1( LN2(x1) ) ) )           (NMP.py:362-363,572-573; timm Mlp)
 // instead of three token GEMMs.  The ablation of the stand-alone GEMMs (tools/gemm_bench.py) showed ~14 us of fill/drain
 // latency per launch and the [T,512] hidden activation (4x the token state, written by fc1 and re-read by fc2) as the
@@ -175,9 +175,12 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long* const tp = (blockIdx.x == 0 && (tid == M_MMA_WARP * 32 || tid == M_MMA2_WARP * 32 || tid == M_EPI_WARP0 * 32)) ? g_trace_m : nullptr;
-  const int Ktot = a.Kx + a.Ke;
-  const int n1 = Ktot / M_BK;                      // phase-1 units per tile
-  const int upt = n1 + 2 * M_NCH;                  // units per tile
+  // phase 1 per tile: n_e k-blocks of E preloaded into acc0 (e_identity: E is the residual, added exactly), then n1 weight
+  // units against the k-blocks of X (and of E when it is an ordinary concatenated operand)
+  const int n_e = a.e_identity ? a.Ke / M_BK : 0;
+  const int n1 = (a.e_identity ? a.Kx : a.Kx + a.Ke) / M_BK;      // phase-1 weight units per tile
+  const int nb = n_e + n1;                         // phase-1 k-blocks the producers handle per tile
+  const int upt = n1 + 2 * M_NCH;                  // weight units per tile
   const int tstep = gridDim.x;
   // every CTA starts at its own rotation of the k-block order (phase 1) and of the hidden-chunk order (phase 3), so that the
   // 148 CTAs do not all pull the same 32 KB of the weight stream at the same time; both are sums: only the fp32 summation
@@ -229,7 +232,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
     auto fetch_next = [&](uint32_t stage) {
       if (f_t < ntiles) {
         const uint32_t dst = smem_u32(sRaw(stage));
-        const int k0 = ((f_kb + rot) % n1) * M_BK;
+        const int k0 = f_kb < n_e ? a.Kx + f_kb * M_BK : ((f_kb - n_e + rot) % n1) * M_BK;
         const bool in_x = k0 + f_c * 4 < a.Kx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -237,7 +240,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
           const float* src = (in_x ? f_x[j] : f_e[j]) + k0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(f_r + 32 * j, f_c)), "l"(ok ? src : a.X), "r"(ok ? 16 : 0));
         }
-        if (++f_kb == n1) { f_kb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
+        if (++f_kb == nb) { f_kb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -245,38 +248,52 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
     uint32_t pu = 0;          // phase-1 units produced so far by this CTA: ring stage pu % 3, A buffer pu & 1, hand-off barrier 1 + pu % 3
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
-      for (int kb = 0; kb < n1; ++kb, ++pu) {
+      for (int kb = 0; kb < nb; ++kb, ++pu) {
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(M_RAW_BAR), "r"(M_PROD) : "memory");
         // the stage consumed one unit ago is free again (every producer is past its reads): re-arm it two k-blocks ahead
         fetch_next((pu + 2) % M_RAW);
         const uint8_t* raw = sRaw(pu % M_RAW);
-        uint32_t hi[16], lo[16];
+        float vv[16];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const float4 v = *reinterpret_cast<const float4*>(raw + swz(a_row, a_c0 + cc));
-          const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float h = rna_tf32_fast(vv[j]);
-            hi[cc * 4 + j] = __float_as_uint(h);
-            lo[cc * 4 + j] = __float_as_uint(vv[j] - h);
-          }
+          vv[cc * 4] = v.x; vv[cc * 4 + 1] = v.y; vv[cc * 4 + 2] = v.z; vv[cc * 4 + 3] = v.w;
         }
-        // A buffer kb % 4 (TMEM columns of the fc1 accumulators and of LN2(x1), both idle in phase 1): free once the MMAs of the
-        // phase-1 unit four back are complete.  The producers wait for the unit THREE back: the `done` barriers rotate with
-        // the three weight slots, and a wait further back could miss its phase (the barrier would already be two ahead).
-        // At the start of a tile: once ALL MMAs of the previous tile are complete (acc0_final)
-        if (kb >= M_NB) {
-          const uint32_t g = (uint32_t)it * upt + kb - M_NB;
-          mbar_wait_warp(&sm.done[g % M_NB], (g / M_NB) & 1);
-        } else if (it > 0 && kb == 0) {
+        // TMEM columns written below were last touched by the previous tile: its MMAs (A buffers alias the fc1 accumulators
+        // and LN2(x1)) and its final epilogue (acc0) must be done
+        if (it > 0 && kb == 0) {
           mbar_wait_warp(&sm.acc0_final, (it - 1) & 1);
+          mbar_wait_warp(&sm.acc0_empty, (it - 1) & 1);
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t ta = tmem + a_lane + abuf_col(kb % M_ABUF) + (uint32_t)(a_c0 * 4);
-        tmem_st16(ta, hi);
-        tmem_st16(ta + 32, lo);
+        if (kb < n_e) {
+          // residual: 16 fp32 values of this row straight into the accumulator columns 32 kb + 4 a_c0 .. + 15
+          uint32_t r[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(vv[i]);
+          tmem_st16(tmem + a_lane + (uint32_t)(kb * M_BK + a_c0 * 4), r);
+        } else {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float h = rna_tf32_fast(vv[i]);
+            hi[i] = __float_as_uint(h);
+            lo[i] = __float_as_uint(vv[i] - h);
+          }
+          // A buffer j % 4 (TMEM columns of the fc1 accumulators and of LN2(x1), both idle in phase 1): free once the MMAs of
+          // the weight unit four back are complete.  The producers wait for the unit THREE back: the `done` barriers rotate
+          // with the three weight slots, and a wait further back could miss its phase (the barrier would be two ahead).
+          const int j = kb - n_e;
+          if (j >= M_NB) {
+            const uint32_t g = (uint32_t)it * upt + j - M_NB;
+            mbar_wait_warp(&sm.done[g % M_NB], (g / M_NB) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
+          const uint32_t ta = tmem + a_lane + abuf_col(j % M_ABUF) + (uint32_t)(a_c0 * 4);
+          tmem_st16(ta, hi);
+          tmem_st16(ta + 32, lo);
+        }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
@@ -361,11 +378,13 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
     if (warp == M_MMA_WARP) {
       for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
         if (it > 0) mbar_wait_warp(&sm.acc0_empty, (it - 1) & 1);         // previous tile's x has been read out of acc0
-        // ---- phase 1: acc0 = [att | x] . [Wproj | I]^T
+        // ---- phase 1: acc0 (= x if the residual was preloaded) += [X | E] . W1cat^T
         g = (uint32_t)it * upt;
-        for (int kb = 0; kb < n1; ++kb, ++pu, ++g) {
+        for (int kb = 0; kb < nb; ++kb, ++pu) {
           mtrace(tp, g * 4 + 0);
           asm volatile("bar.sync %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
+          if (kb < n_e) continue;                                          // a preloaded residual block: nothing to multiply
+          const int j = kb - n_e;
           mtrace(tp, g * 4 + 3);
           wait_b(g);
           mtrace(tp, g * 4 + 1);
@@ -373,21 +392,20 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t bslot = smem_u32(sW(g % M_NB));
             const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + M_TILE);
-            const uint32_t tAh = tmem + abuf_col(kb % M_ABUF), tAl = tAh + 32;
-            // k-blocks of E meet the identity block of the weight, whose lo image is all zero: its A_hi . B_lo product is skipped
-            const bool lo_is_zero = a.e_identity && ((kb + rot) % n1) * M_BK >= a.Kx;
+            const uint32_t tAh = tmem + abuf_col(j % M_ABUF), tAl = tAh + 32;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 2);
-              umma_tf32_ta(acc0, tAl + ks * 8, dBh + adv, idesc128, (kb > 0 || ks > 0) ? 1u : 0u);
-              if (!lo_is_zero) umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
+              umma_tf32_ta(acc0, tAl + ks * 8, dBh + adv, idesc128, (n_e > 0 || j > 0 || ks > 0) ? 1u : 0u);
+              umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
               umma_tf32_ta(acc0, tAh + ks * 8, dBh + adv, idesc128, 1u);
             }
             umma_commit(&sm.done[g % M_NB]);
-            if (kb == n1 - 1) umma_commit(&sm.p1_full);
+            if (j == n1 - 1) umma_commit(&sm.p1_full);
           }
           __syncwarp();
           mtrace(tp, g * 4 + 2);
+          ++g;
         }
         // ---- phase 3, fc2 half: F2(0..15), each as soon as its hidden chunk is in shared memory
         for (int c = 0; c < M_NCH; ++c) {

@@ -191,12 +191,11 @@ class _Launches:
 
     def block_tail(self, what, att, x, rows, proj_w, proj_b, n2, fc1_w, fc1_b, fc2_w, fc2_b):
         """x = x1 + Mlp(LN2(x1)), x1 = x + proj(att): ONE launch of nmrf_mlp_chain (SwinNMP / CSWinNMP tail, NMP.py:358-363,
-        570-573).  The residual stream rides the tensor core as an identity block appended to the proj weight."""
+        570-573).  The residual stream x is preloaded into the fp32 accumulator (e_identity)."""
         from . import ops
         key = (proj_w.data_ptr(), fc1_w.data_ptr(), fc2_w.data_ptr())
         if key not in self._streams:
-            eye = torch.eye(128, device=proj_w.device, dtype=torch.float32)
-            ws = ops.pack_mlp_stream(torch.cat([proj_w, eye], 1).contiguous(), fc1_w.contiguous(), fc2_w.contiguous())
+            ws = ops.pack_mlp_stream(proj_w.contiguous(), fc1_w.contiguous(), fc2_w.contiguous())
             self._streams[key] = (ws, (proj_b + fc2_b).contiguous())
         ws, bias_out = self._streams[key]
         a = MlpArgs()

@@ -105,15 +105,17 @@ def pack_mlp_stream(W1cat, Wfc1, Wfc2):
 
 
 def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_identity=False):
-    """Y = x1 + fc2(GELU(fc1(LN(x1)))) + b_fc2 with x1 = concat(X, E) @ W1cat.T + bias_mid (bias_out = bias_mid + b_fc2);
-    wstream from pack_mlp_stream.  `out` may alias E."""
+    """Y = x1 + fc2(GELU(fc1(LN(x1)))) + b_fc2 (bias_out = bias_mid + b_fc2) with x1 = X @ W1.T + bias_mid + E (e_identity: E is the
+    residual, added exactly) or x1 = concat(X, E) @ W1cat.T + bias_mid; wstream from pack_mlp_stream(W1 or W1cat, ...).
+    `out` may alias E."""
     for n, t in (("X", X), ("E", E), ("wstream", wstream), ("bias_mid", bias_mid), ("gamma", ln[0]), ("beta", ln[1]), ("b1", b1),
                  ("bias_out", bias_out)):
         _chk(t, n)
     rows, Kx = X.shape
     Ke = E.shape[1] if E is not None else 0
-    if wstream.shape != ((Kx + Ke) // 32 + 32, 8192):
-        raise RuntimeError(f"wstream has shape {tuple(wstream.shape)}, expected {((Kx + Ke) // 32 + 32, 8192)}")
+    n1 = (Kx if e_identity else Kx + Ke) // 32
+    if wstream.shape != (n1 + 32, 8192):
+        raise RuntimeError(f"wstream has shape {tuple(wstream.shape)}, expected {(n1 + 32, 8192)}")
     Y = out if out is not None else torch.empty(rows, 128, device=X.device, dtype=torch.float32)
     a = MlpArgs()
     a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), Kx

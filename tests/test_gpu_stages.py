@@ -97,29 +97,31 @@ def test_token_gemm_residual_in_place(ops):
     assert rel_err(y, ref) <= 2e-6
 
 
-@pytest.mark.parametrize("rows,with_proj", [(128, True), (1000, True), (128 * 300 + 5, True), (700, False)])
-def test_mlp_chain(ops, rows, with_proj):
-    """fused block tail (proj + residual + LN2 + fc1 + GELU + fc2 + residual, NMP.py:358-363) against float64"""
+@pytest.mark.parametrize("rows,mode", [(128, "residual"), (1000, "residual"), (128 * 300 + 5, "residual"), (300, "concat"), (700, "mlp")])
+def test_mlp_chain(ops, rows, mode):
+    """fused block tail (proj + residual + LN2 + fc1 + GELU + fc2 + residual, NMP.py:358-363) against float64.
+    residual: x preloaded into the accumulator; concat: x through an identity block of the weight; mlp: Mlp block only."""
     g = torch.Generator().manual_seed(rows)
     att, x = torch.randn(rows, 128, generator=g), 2.0 * torch.randn(rows, 128, generator=g) + 0.3
     Wp, bp = torch.randn(128, 128, generator=g) / 128 ** 0.5, 0.1 * torch.randn(128, generator=g)
     W1, b1 = torch.randn(512, 128, generator=g) / 128 ** 0.5, 0.1 * torch.randn(512, generator=g)
     W2, b2 = torch.randn(128, 512, generator=g) / 512 ** 0.5, 0.1 * torch.randn(128, generator=g)
     gam, bet = 1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
-    if with_proj:
-        x1 = x.double() + att.double() @ Wp.double().T + bp.double()
-        W1cat, X, E, bmid = torch.cat([Wp, torch.eye(128)], 1), att, x, bp
-    else:                                                       # Mlp block only: the identity carries x into the accumulator
+    if mode == "mlp":                                           # Mlp block only: an identity weight carries x into the accumulator
         x1 = x.double()
-        W1cat, X, E, bmid = torch.eye(128), x, None, torch.zeros(128)
+        W1cat, X, E, bmid, ident = torch.eye(128), x, None, torch.zeros(128), False
+    else:
+        x1 = x.double() + att.double() @ Wp.double().T + bp.double()
+        W1cat, X, E, bmid, ident = (Wp, att, x, bp, True) if mode == "residual" else (torch.cat([Wp, torch.eye(128)], 1), att, x, bp, False)
     t = torch.nn.functional.layer_norm(x1, (128,), gam.double(), bet.double(), 1e-5)
     ref = x1 + torch.nn.functional.gelu(t @ W1.double().T + b1.double()) @ W2.double().T + b2.double()
     ws = ops.pack_mlp_stream(cuda(W1cat), cuda(W1), cuda(W2))
     xe = cuda(E) if E is not None else None
-    out = ops.mlp_chain(cuda(X), ws, cuda(bmid), (cuda(gam), cuda(bet)), cuda(b1), cuda(bmid + b2), E=xe)
+    args = (cuda(X), ws, cuda(bmid), (cuda(gam), cuda(bet)), cuda(b1), cuda(bmid + b2))
+    out = ops.mlp_chain(*args, E=xe, e_identity=ident)
     assert rel_err(out, ref) <= 1e-5         # three chained 3xTF32 GEMMs (4e-6 each) + LN + GELU
-    if with_proj:                                               # in place on the residual stream, as the hot path runs it
-        ops.mlp_chain(cuda(X), ws, cuda(bmid), (cuda(gam), cuda(bet)), cuda(b1), cuda(bmid + b2), E=xe, out=xe, e_identity=True)
+    if mode == "residual":                                      # in place on the residual stream, as the hot path runs it
+        ops.mlp_chain(*args, E=xe, out=xe, e_identity=True)
         assert rel_err(xe, ref) <= 1e-5
 
 

@@ -40,15 +40,16 @@ print(f"DBG={os.environ.get('NMRF_B200_DBG', '0'):>2s} V={os.environ.get('NMRF_B
 for rows in (34560, 32640):
     att, x = torch.randn(rows, 128, generator=g).to(dev), torch.randn(rows, 128, generator=g).to(dev)
     Wp, W1, W2 = (torch.randn(128, 128, generator=g) / 11).to(dev), (torch.randn(512, 128, generator=g) / 11).to(dev), (torch.randn(128, 512, generator=g) / 22).to(dev)
-    ws = ops.pack_mlp_stream(Wp.contiguous(), W1, W2)
+    PRELOAD = os.environ.get('NMRF_B200_RESIDUAL', 'preload') != 'identity'
+    ws = ops.pack_mlp_stream(Wp.contiguous() if PRELOAD else torch.cat([Wp, torch.eye(128, device=dev)], 1).contiguous(), W1, W2)
     z, o, b1 = torch.zeros(128, device=dev), torch.ones(128, device=dev), torch.zeros(512, device=dev)
     for _ in range(3):
-        ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x, e_identity=True)
+        ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x, e_identity=PRELOAD)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(reps):
-        ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x, e_identity=True)
+        ops.mlp_chain(att, ws, z, (o, z), b1, z, E=x, out=x, e_identity=PRELOAD)
     e.record(); torch.cuda.synchronize()
     us = s.elapsed_time(e) * 1e3 / reps
-    units = ((rows + 127) // 128) * 36
+    units = ((rows + 127) // 128) * (36 if PRELOAD else 40)
     print(f"mlp_chain rows={rows}: {us:6.1f}us ({us * 1.9e3 * 148 / units:5.0f} cyc/unit/SM; replaces proj+fc1+fc2)")

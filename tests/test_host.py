@@ -101,3 +101,23 @@ def test_param_containers_do_not_compute():
     model, _ = build_product_model(64, 2, (1, 1, 1), 0, "reference")
     with pytest.raises(RuntimeError, match="libnmrf_b200"):
         model.inference(torch.zeros(1))
+
+
+def test_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the oracle port on the host cores, no GPU involved) prints ONE JSON line with the keys
+    the driver reads; same metric / unit / workload as the B200 arm."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("stereo pairs/sec at 960x540") and d["config"]["workload"] == "sceneflow_540x960_D192_K4_L8"
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

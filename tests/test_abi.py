@@ -54,3 +54,33 @@ def test_struct_layout_matches_c():
     assert ctypes.sizeof(_lib.GemmArgs) == 144
     # X,ldx,Kx | E,lde,Ke | Wstream | bias_mid | g,b | b1 | bias_out | Y,ldy,rows | e_identity (+pad)
     assert ctypes.sizeof(_lib.MlpArgs) == 104
+
+
+def test_struct_field_offsets_match_a_c_compiler(tmp_path):
+    """compile include/nmrf_b200.h as plain C (gcc) and compare offsetof() of every struct field with the ctypes mirrors"""
+    import shutil
+    import subprocess
+    from nmrf_b200 import _lib
+    if shutil.which("gcc") is None:
+        import pytest
+        pytest.skip("no gcc")
+    structs = {"nmrf_gemm_args": _lib.GemmArgs, "nmrf_mlp_args": _lib.MlpArgs, "nmrf_seed_weights": _lib.SeedWeights}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "nmrf_b200.h")}"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", str(src), "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    seen = 0
+    for line in out.strip().splitlines():
+        cname, fname, val = line.split()
+        ct = structs[cname]
+        want = ctypes.sizeof(ct) if fname == "size" else getattr(ct, fname).offset
+        assert int(val) == want, f"{cname}.{fname}: C says {val}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(ct._fields_) + 1 for ct in structs.values())

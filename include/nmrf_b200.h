@@ -12,8 +12,15 @@
  *
  * Packed weights: the reference's nn.Linear weights ([out,in] row-major) are used as they are,
  * except that the input dimension is zero-padded to a multiple of 16 and q/k/v projections
- * that share an input are stacked along `out` (see nmrf_b200/plan.py, which does the packing
- * with torch ops at load time; layouts are documented per struct below).
+ * that share an input are stacked along `out` (see nmrf_b200/hotpath.py: PackedWeights, which does
+ * the packing with torch ops at load time; layouts are documented per struct below).
+ *
+ * Extended labels.  The disparity labels that travel between stages (`labels` after the propagation head, `disp_curr`
+ * after the selection) feed Fourier features with frequencies up to 2^14 (NMP.py:42-48): one fp32 ulp of a label
+ * (~2e-6 px) is ~1.5e-3 rad in the top frequency, the largest single rounding effect of the reference's fp32 forward and
+ * a source of flipped argmax / median decisions (NMRF.py:228-231).  Every entry point that produces or consumes a label
+ * therefore takes an optional `*_lo` pointer: label = hi + lo (two fp32 words, the sum formed in double).  `*_lo == NULL`
+ * reproduces the reference's plain fp32 arithmetic; the `hi` word alone is always the fp32 value the reference returns.
  */
 #ifndef NMRF_B200_H
 #define NMRF_B200_H
@@ -24,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NMRF_B200_ABI_VERSION 6
+#define NMRF_B200_ABI_VERSION 7
 
 enum {
   NMRF_OK = 0,
@@ -60,14 +67,11 @@ typedef struct {
   float* Y; int ldy;
   int rows; int N;
   int act;                                     /* 0 none, 1 ReLU, 2 GELU (erf) */
-  /* Tensor-core path (tcgen05 kind::tf32, error-compensated 3xTF32, fp32-level accuracy): set W to the
-   * hi part and W_lo to the lo part produced by nmrf_split_tf32 from a weight whose input dimension is
-   * zero-padded to a multiple of 32 (ldw % 32 == 0); N % 16 == 0, N <= 512.  W_lo == NULL selects the
-   * exact-fp32 FMA kernel. */
-  const float* W_lo;
-  /* Optional (preferred by the tensor-core path): the same hi / lo weights as TILE IMAGES produced by
-   * nmrf_pack_weight_tiles -- [ceil(N/128)][ceil(K/32)] tiles of 128 rows x 32 fp32, each tile stored exactly as its
-   * SWIZZLE_128B shared-memory image (16 KB), so a tile is fetched with one TMA bulk copy (cp.async.bulk). */
+  /* Tensor-core path (tcgen05 kind::tf32, error-compensated 3xTF32 with round-to-nearest hi AND lo operand parts,
+   * fp32-level accuracy): the weight as hi / lo TILE IMAGES produced by nmrf_pack_weight_tiles --
+   * [ceil(N/128)][ceil(K/32)] tiles of 128 rows x 32 fp32, each tile stored exactly as its SWIZZLE_128B shared-memory
+   * image (16 KB), so a tile is fetched with one TMA bulk copy (cp.async.bulk).  N % 16 == 0, N <= 512; W may then be
+   * NULL.  Wt_hi == Wt_lo == NULL selects the exact-fp32 FMA kernel on W. */
   const float* Wt_hi;
   const float* Wt_lo;
 } nmrf_gemm_args;
@@ -101,7 +105,8 @@ typedef struct {
 } nmrf_mlp_args;
 int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream);
 
-/* debug tooling: device buffer of 4096 int64 that CTA 0 of the tensor-core GEMM fills with clock64() stamps (NULL = off) */
+/* debug tooling: device buffer of 4096 int64 that CTA 0 of the tensor-core GEMMs fills with clock64() stamps (NULL = off).
+ * Only in builds made with `make TRACE=1`; release builds carry no tracing code and return NMRF_ERR_UNSUPPORTED. */
 int nmrf_debug_set_trace(void* dev_i64_4096);
 /* hi = rna_tf32(w), lo = rna_tf32(w - hi), elementwise over n floats (device pointers) */
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
@@ -131,7 +136,8 @@ int nmrf_cost_volume_topk(const float* f1_nhwc, const float* f2_nhwc,   /* [B,h,
  * enc row layout: 15 sin, 15 cos, raw coordinate, then zero up to 32.
  */
 int nmrf_prop_gather(const float* cost_volume, const int64_t* seeds, int P, int G, int D, int K,
-                     float normalizer,
+                     double normalizer,
+                     int extended,                /* 1: encoding evaluated in double (see "Extended labels"), 0: fp32 as the reference */
                      float* cost36, int ld_cost,  /* [P*K, ld_cost] */
                      float* enc32,                /* [P*K, 32] */
                      void* stream);
@@ -149,7 +155,8 @@ int nmrf_stripe_attention(const float* qkv, int B, int h, int w, int K,
 /* ---- A7 tail: labels = relu(hidden . w + b + seed) ------------------------------------------
  * last layer of dpn.prop_head (DPN.py:65,131-132). hidden: [T,128] (after the two ReLU layers). */
 int nmrf_prop_head_tail(const float* hidden, const float* w /*[128]*/, const float* b /*[1]*/,
-                        const int64_t* seeds, int T, float* labels /*[T]*/, void* stream);
+                        const int64_t* seeds, int T, float* labels /*[T]*/, float* labels_lo /*[T] or NULL*/,
+                        void* stream);
 
 /* ---- A8: warp + group-wise correlation + Fourier embed ---------------------------------------
  * replaces Inference.sample_fmap/corr (NMP.py:682-720,735-743) and Refinement's K=1 case
@@ -160,8 +167,9 @@ int nmrf_prop_head_tail(const float* hidden, const float* w /*[128]*/, const flo
 int nmrf_warp_corr_embed(const float* f1_cc, const float* f2_cc,   /* [B,h,w,64]  NHWC */
                          const float* f1_gw, const float* f2_gw,   /* [B,h,w,256] NHWC */
                          const float* labels,                      /* [B*h*w, K] */
+                         const float* labels_lo,                   /* [B*h*w, K] or NULL */
                          int B, int h, int w, int K, int Hp, int Wp, int top, int left,
-                         float normalizer,
+                         double normalizer,
                          float* feat160, float* enc32,             /* [B*Hp*Wp*K, 160 | 32] */
                          void* stream);
 /* zero the rows of x[B*Hp*Wp*K, 128] that are padding (label_rep is padded AFTER ffn) */
@@ -189,14 +197,18 @@ int nmrf_window_attention(const float* qkv, const float* table,
  * labels [B*h*w, K].  disp_curr [B, 2h, 2w] (units: 1/4-res pixels).
  */
 int nmrf_select_median(const float* delta, const float* score, const float* labels,
+                       const float* labels_lo,     /* [B*h*w, K] or NULL */
                        int B, int h, int w, int K, int Hp, int Wp, int top, int left,
-                       float* disp_curr, void* stream);
+                       float* disp_curr,
+                       float* disp_curr_lo,        /* [B, 2h, 2w]; NULL iff labels_lo is NULL */
+                       void* stream);
 
 /* ---- A13 tail: disp = relu(disp_curr + delta) un-shuffled -------------------------------------
  * replaces NMRF.py:238-245,250-251. delta [B*Hp4*Wp4, 16] on the padded 1/4 grid;
  * disp_pred [B, 4*h4, 4*w4] (1/4-res units), disp [B, H, W] = 4*disp_pred cropped (unpad).
  */
 int nmrf_refine_tail(const float* delta, const float* disp_curr,
+                     const float* disp_curr_lo,    /* [B, h4, w4] or NULL */
                      int B, int h4, int w4, int Hp4, int Wp4, int top, int left, int H, int W,
                      float* disp_pred, float* disp, void* stream);
 

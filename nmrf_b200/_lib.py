@@ -5,11 +5,12 @@ module raises, and every entry point raises RuntimeError on a non-zero return co
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnmrf_b200.so")
-ABI_VERSION = 6
+# NMRF_B200_LIB: development override (A/B of two builds of the SAME library, e.g. `make LO_TRUNC=1 LIB=...`); not a fallback
+LIB_PATH = os.environ.get("NMRF_B200_LIB") or os.path.join(_HERE, "libnmrf_b200.so")
+ABI_VERSION = 7
 
 
 class GemmArgs(Structure):
@@ -24,7 +25,6 @@ class GemmArgs(Structure):
         ("Y", c_void_p), ("ldy", c_int),
         ("rows", c_int), ("N", c_int),
         ("act", c_int),
-        ("W_lo", c_void_p),
         ("Wt_hi", c_void_p), ("Wt_lo", c_void_p),
     ]
 
@@ -51,7 +51,7 @@ class SeedWeights(Structure):
 
 
 # name -> argtypes; every function returns int except the three helpers
-_I, _F, _P = c_int, c_float, c_void_p
+_I, _F, _D, _P = c_int, c_float, c_double, c_void_p
 SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
     "nmrf_mlp_chain": [POINTER(MlpArgs), _P],
@@ -65,15 +65,15 @@ SIGNATURES = {
     "nmrf_debug_set_trace": [_P],
     "nmrf_pack_weight_tiles": [_P, _I, _I, _P, _P, _P],
     "nmrf_cost_volume_topk": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _F, POINTER(SeedWeights), _P, _P, _P, _P],
-    "nmrf_prop_gather": [_P, _P, _I, _I, _I, _I, _F, _P, _I, _P, _P],
+    "nmrf_prop_gather": [_P, _P, _I, _I, _I, _I, _D, _I, _P, _I, _P, _P],
     "nmrf_stripe_attention": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
-    "nmrf_prop_head_tail": [_P, _P, _P, _P, _I, _P, _P],
-    "nmrf_warp_corr_embed": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _F, _P, _P, _P],
+    "nmrf_prop_head_tail": [_P, _P, _P, _P, _I, _P, _P, _P],
+    "nmrf_warp_corr_embed": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _D, _P, _P, _P],
     "nmrf_zero_pad_rows": [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     "nmrf_proposal_attention": [_P, _I, _I, _P, _P],
     "nmrf_window_attention": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
-    "nmrf_select_median": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P],
-    "nmrf_refine_tail": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "nmrf_select_median": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "nmrf_refine_tail": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "nmrf_ms_deform_attn_forward": [_P, POINTER(c_int64), POINTER(c_int64), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "nmrf_ms_deform_attn_forward_dev": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
 }

@@ -58,14 +58,47 @@ def get_cfg():
     return CfgNode._wrap(copy.deepcopy(_DEFAULTS))
 
 
+def create_backbone(cfg):
+    """`create_backbone` of the reference (nmrf/models/backbone.py:176-200).  The ResNet-style encoder is built here; the
+    Swin-T + DeformNeck encoder is the REFERENCE's own torch module (outside the hot path), constructed from the
+    reference tree when it is importable, with `nmrf_b200.msda` installed as its `MultiScaleDeformableAttention` extension --
+    the one native op of that encoder (boundary B2)."""
+    import torch.nn as nn
+    from .backbone import Backbone
+    model_type = cfg.BACKBONE.MODEL_TYPE
+    if model_type == "resnet":
+        if cfg.BACKBONE.NORM_FN == "instance":
+            norm_layer = nn.InstanceNorm2d
+        elif cfg.BACKBONE.NORM_FN == "batch":
+            norm_layer = nn.BatchNorm2d
+        else:
+            raise ValueError(f"Invalid backbone normalization type: {cfg.BACKBONE.NORM_FN}")
+        return Backbone(cfg.BACKBONE.OUT_CHANNELS, norm_layer)
+    if model_type == "swin":
+        from . import msda
+        msda.install_as_reference_extension()
+        try:
+            from nmrf.models.backbone import SwinAdaptor          # the reference's module, unmodified
+        except Exception as e:                                     # not on sys.path, or its own dependencies are missing
+            raise NotImplementedError(
+                "BACKBONE.MODEL_TYPE='swin' uses the reference's SwinAdaptor (nmrf/models/backbone.py:101-158): put the reference "
+                f"tree on sys.path (and its dependencies, e.g. timm) -- import failed with: {e!r}") from e
+        backbone = SwinAdaptor(out_channels=cfg.BACKBONE.OUT_CHANNELS, drop_path_rate=cfg.BACKBONE.DROP_PATH)
+        if cfg.BACKBONE.WEIGHT_URL:
+            import torch
+            weight = torch.load(cfg.BACKBONE.WEIGHT_URL, map_location="cpu")
+            weight = weight.get("model", weight)
+            weight = weight.get("state_dict", weight)
+            weight = {k: v for k, v in weight.items() if "attn_mask" not in k and not k.startswith(("norm", "head"))}
+            backbone.backbone.load_state_dict(weight)
+        return backbone
+    raise ValueError(f"Do not find {model_type}")
+
+
 def build_model(cfg):
     """`nmrf.models.build_model` (models/__init__.py:9-10) without the training criterion."""
-    from .backbone import Backbone
     from .model import DPN, NMRF
-    if cfg.BACKBONE.MODEL_TYPE != "resnet":
-        raise NotImplementedError("build_model constructs the ResNet encoder; pass your own encoder to NMRF(backbone=...) "
-                                  "(e.g. the reference SwinAdaptor with nmrf_b200.msda as its MSDeformAttn op)")
-    backbone = Backbone(cfg.BACKBONE.OUT_CHANNELS)
+    backbone = create_backbone(cfg)
     dpn = DPN(cost_group=cfg.DPN.COST_GROUP, num_proposals=cfg.DPN.NUM_PROPOSALS, feat_dim=cfg.BACKBONE.OUT_CHANNELS,
               context_dim=cfg.DPN.CONTEXT_DIM, num_prop_layers=cfg.NMP.NUM_PROP_LAYERS,
               prop_embed_dim=cfg.NMP.PROP_EMBED_DIM, mlp_ratio=cfg.NMP.MLP_RATIO, split_size=cfg.NMP.SPLIT_SIZE,

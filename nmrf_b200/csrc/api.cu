@@ -17,6 +17,19 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int num_sms() {
+  static PerDevice cache;
+  const int d = current_device();
+  if (d >= 0 && d < kMaxDevices) {
+    const int c = cache.v[d].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int n = 0;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d);
+  if (n <= 0) n = 148;
+  if (d >= 0 && d < kMaxDevices) cache.v[d].store(n, std::memory_order_relaxed);
+  return n;
+}
 int check_launch(const char* what) {
   const cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) return NMRF_OK;
@@ -25,21 +38,16 @@ int check_launch(const char* what) {
 }
 
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
-int token_gemm_tc(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
-int token_gemm_tc5(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
-int gemm_set_trace(long long* dev_ptr);
-int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream);
+int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
-int token_gemm_ws(const nmrf_gemm_args& a, cudaStream_t stream);
-bool token_gemm_ws_supported(const nmrf_gemm_args& a);
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
 int mlp_set_trace(long long* dev_ptr);
 int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
                      float*, float*, int64_t*, cudaStream_t);
-int prop_gather(const float*, const int64_t*, int, int, int, int, float, float*, int, float*, cudaStream_t);
-int prop_head_tail(const float*, const float*, const float*, const int64_t*, int, float*, cudaStream_t);
+int prop_gather(const float*, const int64_t*, int, int, int, int, double, int, float*, int, float*, cudaStream_t);
+int prop_head_tail(const float*, const float*, const float*, const int64_t*, int, float*, float*, cudaStream_t);
 int proposal_attention(const float*, int, int, float*, cudaStream_t);
 int window_attention(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int stripe_attention(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
@@ -51,11 +59,12 @@ int split_cat3(const float*, long long, int, float*, cudaStream_t);
 int image_prep(const float*, const float*, int, int, int, float*, cudaStream_t);
 int avgpool2_split(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
 int window_attention_mma(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
-int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, int, int, int, int, int, int,
-                    int, int, float, float*, float*, cudaStream_t);
+int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int, int,
+                    int, int, int, double, float*, float*, cudaStream_t);
 int zero_pad_rows(float*, int, int, int, int, int, int, int, int, cudaStream_t);
-int select_median(const float*, const float*, const float*, int, int, int, int, int, int, int, int, float*, cudaStream_t);
-int refine_tail(const float*, const float*, int, int, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int select_median(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, int, float*, float*,
+                  cudaStream_t);
+int refine_tail(const float*, const float*, const float*, int, int, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
 int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const float*, const float*, int, int, int, int,
                            int, int, int, float*, bool, cudaStream_t);
 
@@ -63,7 +72,7 @@ int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const f
 
 using namespace nmrf;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
-static_assert(sizeof(nmrf_gemm_args) == 144 && sizeof(nmrf_mlp_args) == 104, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
+static_assert(sizeof(nmrf_gemm_args) == 136 && sizeof(nmrf_mlp_args) == 104, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
 
 // NMRF_B200_ATTN=simt selects the fp32-FMA attention kernels (default: tcgen05 3xTF32)
 static std::atomic<int> g_attn_tc{-1};
@@ -84,10 +93,10 @@ const char* nmrf_last_error(void) { return g_err; }
 uint64_t nmrf_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
-  NMRF_REQUIRE(a && a->X && a->W && a->Y, "token_gemm: null pointer");
+  NMRF_REQUIRE(a && a->X && a->Y && (a->W || a->Wt_hi), "token_gemm: null pointer");
   NMRF_REQUIRE(a->rows >= 0 && a->N > 0 && a->N % 4 == 0, "token_gemm: rows=%d N=%d (N must be a multiple of 4)", a->rows, a->N);
   NMRF_REQUIRE(a->Kx > 0 && a->Kx % 8 == 0 && a->Ke >= 0 && a->Ke % 8 == 0, "token_gemm: Kx=%d Ke=%d must be multiples of 8", a->Kx, a->Ke);
-  NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldw % 4 == 0 && a->ldy % 4 == 0 && a->ldw >= a->Kx + a->Ke, "token_gemm: bad leading dimension");
+  NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldy % 4 == 0 && (a->Wt_hi || (a->ldw % 4 == 0 && a->ldw >= a->Kx + a->Ke)), "token_gemm: bad leading dimension");
   NMRF_REQUIRE((a->Ke == 0) == (a->E == nullptr), "token_gemm: E/Ke mismatch");
   NMRF_REQUIRE(a->Ke == 0 || (a->ediv >= 1 && a->lde % 4 == 0), "token_gemm: bad ediv/lde");
   NMRF_REQUIRE((a->ln_gamma == nullptr) == (a->ln_beta == nullptr), "token_gemm: LayerNorm needs gamma and beta");
@@ -95,19 +104,10 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
   NMRF_REQUIRE(a->R == nullptr || a->ldr % 4 == 0, "token_gemm: bad ldr");
   NMRF_REQUIRE(a->act >= 0 && a->act <= 2, "token_gemm: act=%d", a->act);
   if (a->rows == 0) return NMRF_OK;
-  if (a->W_lo) {
-    const int kpad = ((a->Kx + a->Ke + 31) / 32) * 32;
+  NMRF_REQUIRE((a->Wt_hi == nullptr) == (a->Wt_lo == nullptr), "token_gemm: Wt_hi and Wt_lo go together");
+  if (a->Wt_hi) {
     NMRF_REQUIRE(a->N % 16 == 0 && a->N <= 512, "token_gemm(tc): N=%d must be a multiple of 16, <= 512", a->N);
-    NMRF_REQUIRE(a->ldw % 32 == 0 && a->ldw >= kpad, "token_gemm(tc): ldw=%d must be a multiple of 32 and >= %d", a->ldw, kpad);
-    // NMRF_B200_GEMM_V selects an older schedule of the same arithmetic (4: single-role, 5: A operand in shared memory)
-    static const int ver = [] { const char* e = getenv("NMRF_B200_GEMM_V"); return (e && e[0] >= '4' && e[0] <= '6') ? e[0] - '0' : 6; }();
-    // experiment (NMRF_B200_GEMM_WS=1): K <= 192 with the weights stationary in tensor memory (gemm_ws.cu); correct, but
-    // 54 vs 44 us for the qkv projection -- weight traffic is not what bounds these GEMMs
-    static const int ws = [] { const char* e = getenv("NMRF_B200_GEMM_WS"); return (e && e[0] == '1') ? 1 : 0; }();
-    if (ws && ver == 6 && token_gemm_ws_supported(*a)) return token_gemm_ws(*a, ST(stream));
-    if (ver == 4) return token_gemm_tc(*a, a->W_lo, ST(stream));
-    if (ver == 5 || !a->Wt_hi || !a->Wt_lo) return token_gemm_tc5(*a, a->W_lo, ST(stream));
-    return token_gemm_tc6(*a, a->W_lo, ST(stream));
+    return token_gemm_tc6(*a, ST(stream));
   }
   return token_gemm_simt(*a, ST(stream));
 }
@@ -131,9 +131,14 @@ int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float*
   return pack_weight_tiles(w, N, K, hi_tiles, lo_tiles, ST(stream));
 }
 int nmrf_debug_set_trace(void* dev_i64_4096) {
-  gemm_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
+#ifdef NMRF_TRACE
   mlp_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
   return gemm6_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
+#else
+  if (dev_i64_4096 == nullptr) return NMRF_OK;
+  set_error("nmrf_debug_set_trace: this build has no cycle tracing (rebuild with make TRACE=1)");
+  return NMRF_ERR_UNSUPPORTED;
+#endif
 }
 int nmrf_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
   return split_tf32(w, hi, lo, (long long)n, ST(stream));
@@ -143,9 +148,9 @@ int nmrf_cost_volume_topk(const float* f1, const float* f2, int B, int h, int w,
                           const nmrf_seed_weights* wt, float* cost_volume, float* prob, int64_t* seeds, void* stream) {
   return cost_volume_topk(f1, f2, B, h, w, C, G, D, K, eps, wt, cost_volume, prob, seeds, ST(stream));
 }
-int nmrf_prop_gather(const float* cv, const int64_t* seeds, int P, int G, int D, int K, float normalizer, float* cost36,
-                     int ld_cost, float* enc32, void* stream) {
-  return prop_gather(cv, seeds, P, G, D, K, normalizer, cost36, ld_cost, enc32, ST(stream));
+int nmrf_prop_gather(const float* cv, const int64_t* seeds, int P, int G, int D, int K, double normalizer, int extended,
+                     float* cost36, int ld_cost, float* enc32, void* stream) {
+  return prop_gather(cv, seeds, P, G, D, K, normalizer, extended, cost36, ld_cost, enc32, ST(stream));
 }
 int nmrf_stripe_attention(const float* qkv, int B, int h, int w, int K, const float* gv0, const float* gv1, float* out,
                           void* stream) {
@@ -158,14 +163,14 @@ int nmrf_stripe_attention(const float* qkv, int B, int h, int w, int K, const fl
   return stripe_attention(qkv, B, h, w, K, gv0, gv1, out, ST(stream));
 }
 int nmrf_prop_head_tail(const float* hidden, const float* w, const float* b, const int64_t* seeds, int T, float* labels,
-                        void* stream) {
-  return prop_head_tail(hidden, w, b, seeds, T, labels, ST(stream));
+                        float* labels_lo, void* stream) {
+  return prop_head_tail(hidden, w, b, seeds, T, labels, labels_lo, ST(stream));
 }
 int nmrf_warp_corr_embed(const float* f1_cc, const float* f2_cc, const float* f1_gw, const float* f2_gw,
-                         const float* labels, int B, int h, int w, int K, int Hp, int Wp, int top, int left,
-                         float normalizer, float* feat160, float* enc32, void* stream) {
-  return warp_corr_embed(f1_cc, f2_cc, f1_gw, f2_gw, labels, B, h, w, K, Hp, Wp, top, left, normalizer, feat160, enc32,
-                         ST(stream));
+                         const float* labels, const float* labels_lo, int B, int h, int w, int K, int Hp, int Wp, int top,
+                         int left, double normalizer, float* feat160, float* enc32, void* stream) {
+  return warp_corr_embed(f1_cc, f2_cc, f1_gw, f2_gw, labels, labels_lo, B, h, w, K, Hp, Wp, top, left, normalizer, feat160,
+                         enc32, ST(stream));
 }
 int nmrf_zero_pad_rows(float* x, int B, int h, int w, int K, int Hp, int Wp, int top, int left, void* stream) {
   return zero_pad_rows(x, B, h, w, K, Hp, Wp, top, left, ST(stream));
@@ -199,13 +204,13 @@ int nmrf_image_prep(const float* img1_nhwc, const float* img2_nhwc, int B, int H
 int nmrf_avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_cat3, void* stream) {
   return avgpool2_split(x, N, h, w, C, out_a, out_b, out_cat3, ST(stream));
 }
-int nmrf_select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K, int Hp,
-                       int Wp, int top, int left, float* disp_curr, void* stream) {
-  return select_median(delta, score, labels, B, h, w, K, Hp, Wp, top, left, disp_curr, ST(stream));
+int nmrf_select_median(const float* delta, const float* score, const float* labels, const float* labels_lo, int B, int h,
+                       int w, int K, int Hp, int Wp, int top, int left, float* disp_curr, float* disp_curr_lo, void* stream) {
+  return select_median(delta, score, labels, labels_lo, B, h, w, K, Hp, Wp, top, left, disp_curr, disp_curr_lo, ST(stream));
 }
-int nmrf_refine_tail(const float* delta, const float* disp_curr, int B, int h4, int w4, int Hp4, int Wp4, int top, int left,
-                     int H, int W, float* disp_pred, float* disp, void* stream) {
-  return refine_tail(delta, disp_curr, B, h4, w4, Hp4, Wp4, top, left, H, W, disp_pred, disp, ST(stream));
+int nmrf_refine_tail(const float* delta, const float* disp_curr, const float* disp_curr_lo, int B, int h4, int w4, int Hp4,
+                     int Wp4, int top, int left, int H, int W, float* disp_pred, float* disp, void* stream) {
+  return refine_tail(delta, disp_curr, disp_curr_lo, B, h4, w4, Hp4, Wp4, top, left, H, W, disp_pred, disp, ST(stream));
 }
 int nmrf_ms_deform_attn_forward(const float* value, const int64_t* shapes, const int64_t* level_start, const float* loc,
                                 const float* attn, int N, int S, int M, int Dh, int L, int Lq, int P, float* out,

@@ -448,11 +448,8 @@ int proposal_attention(const float* qkv, int P, int K, float* out, cudaStream_t 
 
 template <int R, int NCH>
 static int launch_window(const WinParams& p, size_t smem, dim3 grid, cudaStream_t stream) {
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(window_attention_kernel<R, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static PerDevice configured;
+  ensure_dynamic_smem(window_attention_kernel<R, NCH>, (int)smem, configured);
   window_attention_kernel<R, NCH><<<grid, WIN_THREADS, smem, stream>>>(p);
   count_launch();
   return check_launch("window_attention");

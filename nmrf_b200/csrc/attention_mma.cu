@@ -36,12 +36,12 @@ struct WinMmaParams {
   int B, Hp, Wp, shift, self_edge, nwy, nwx, nwin;
 };
 
-// hi = x rounded to nearest tf32; lo = x - hi handed over unrounded: the tensor core reads only the upper 19 bits, and
-// truncating lo loses at most 2^-13 |lo| <= 2^-25 |x|
+// hi = x rounded to nearest tf32; lo = x - hi (exact) rounded to nearest tf32 as well: mma.sync reads only the upper 19 bits
+// of an operand, i.e. it would TRUNCATE an unrounded lo (tc_common.cuh: lo_tf32)
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
   const float h = rna_tf32_fast(x);
   hi = __float_as_uint(h);
-  lo = __float_as_uint(x - h);
+  lo = __float_as_uint(tc::lo_tf32(x, h));
 }
 __device__ __forceinline__ void mma8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -348,11 +348,8 @@ int launch_mma(const WinMmaParams& p, cudaStream_t stream) {
   constexpr int TAB = 2 * G::NR * LD, VSZ = WPC * G::Tw * LD;
   constexpr size_t smem = sizeof(float) * ((size_t)WPC * G::Tw * LD + (size_t)WPC * G::Tw * G::PS + (size_t)NWARP * 16 * G::PS +
                                            (TAB > VSZ ? TAB : VSZ)) + sizeof(int) * (WPC * G::Tw + WPC * G::P);
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(window_attention_mma_kernel<WS, K, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = true;
-  }
+  static PerDevice configured;
+  ensure_dynamic_smem(window_attention_mma_kernel<WS, K, WPC, MINB>, (int)smem, configured);
   dim3 grid((p.nwin + WPC - 1) / WPC, kHeads);
   window_attention_mma_kernel<WS, K, WPC, MINB><<<grid, NWARP * 32, smem, stream>>>(p);
   count_launch();

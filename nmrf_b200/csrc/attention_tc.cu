@@ -44,11 +44,11 @@ struct AtSmem {
   float gv[3][32];          // LePE taps (prev, centre, next) of this head's 32 channels
 };
 
-// hi = x rounded to TF32 (nearest, two integer ops), lo = x - hi exactly (the tensor core truncates lo to TF32, losing
-// <= 2^-21 |lo|): 3 instructions per element instead of 9 with two cvt.rna -- the kernel is issue-bound on this split
+// hi = x rounded to TF32 (nearest, two integer ops), lo = x - hi (exact) rounded the same way (tc_common.cuh: lo_tf32; the
+// tensor core would truncate an unrounded lo): 5 instructions per element instead of 9 with two cvt.rna
 __device__ __forceinline__ void split4(const float4 v, float4& h, float4& l) {
   h.x = rna_tf32_fast(v.x); h.y = rna_tf32_fast(v.y); h.z = rna_tf32_fast(v.z); h.w = rna_tf32_fast(v.w);
-  l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+  l.x = lo_tf32(v.x, h.x); l.y = lo_tf32(v.y, h.y); l.z = lo_tf32(v.z, h.z); l.w = lo_tf32(v.w, h.w);
 }
 __device__ __forceinline__ uint32_t idesc_n(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -269,7 +269,7 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
         const float x = s[g16 * 16 + j];
         const float hv = rna_tf32_fast(x);
         hi[j] = __float_as_uint(hv);
-        lo[j] = __float_as_uint(x - hv);
+        lo[j] = __float_as_uint(lo_tf32(x, hv));
       }
       tmem_st16(tmem + t_lane + (uint32_t)(AT_COL_PH + g16 * 16), hi);
       tmem_st16(tmem + t_lane + (uint32_t)(AT_COL_PL + g16 * 16), lo);
@@ -348,11 +348,8 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
 namespace {
 template <int KC>
 int launch_stripe(const float* qkv, int B, int h, int w, int K, const float* get_v0, const float* get_v1, float* out, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(stripe_attention_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, AtCfg<KC>::DYN);
-    configured = true;
-  }
+  static PerDevice configured;
+  ensure_dynamic_smem(stripe_attention_tc_kernel<KC>, AtCfg<KC>::DYN, configured);
   const int Lmax = (h > w ? h : w) * K;
   const int smax = B * (h > w ? h : w);
   dim3 grid((Lmax + 127) / 128, smax, kHeads);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <math.h>
+#include <atomic>
 #include "../../include/nmrf_b200.h"
 
 namespace nmrf {
@@ -17,6 +18,21 @@ constexpr int kMaxK = 8;        // proposals per pixel supported by the small-K 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> NMRF_ERR_CUDA + message
 void count_launch(int n = 1);
+
+// Per-device launch configuration.  cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count are properties of a
+// (kernel, device) pair: a process that drives several GPUs must configure each of them (one static flag per kernel would
+// leave every device but the first with the 48 KB default and fail the launch).  Races are benign (idempotent calls).
+constexpr int kMaxDevices = 64;
+struct PerDevice { std::atomic<int> v[kMaxDevices]; };      // zero-initialised statics
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
+int num_sms();                                                // SM count of the current device (api.cu)
+template <typename Kernel>
+inline void ensure_dynamic_smem(Kernel kernel, int bytes, PerDevice& done) {
+  const int d = current_device();
+  if (d >= 0 && d < kMaxDevices && done.v[d].load(std::memory_order_relaxed) >= bytes) return;
+  cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (d >= 0 && d < kMaxDevices) done.v[d].store(bytes, std::memory_order_relaxed);
+}
 
 #define NMRF_REQUIRE(cond, ...)                       \
   do {                                                \
@@ -47,6 +63,19 @@ __device__ __forceinline__ void fourier32(float coord, float normalizer, float* 
   if (lane < 15) v = sinf(c * exp2f((float)lane));
   else if (lane < 30) v = cosf(c * exp2f((float)(lane - 15)));
   else if (lane == 30) v = c;
+  else v = 0.f;
+  dst[lane] = v;
+}
+
+// Same encoding from an EXTENDED-precision coordinate (label = hi + lo, see nmrf_prop_head_tail): the argument c * 2^i is
+// formed and reduced in double, so the top frequencies (c * 2^14 ~ 2e4 rad, where one fp32 ulp of the label is ~1.5e-3 rad)
+// are as accurate as the coordinate itself.  30 double sin/cos per token: noise next to the projections that consume them.
+__device__ __forceinline__ void fourier32_ext(double coord, double normalizer, float* __restrict__ dst, int lane) {
+  const double c = coord * normalizer;
+  float v;
+  if (lane < 15) v = (float)sin(c * (double)(1 << lane));
+  else if (lane < 30) v = (float)cos(c * (double)(1 << (lane - 15)));
+  else if (lane == 30) v = (float)c;
   else v = 0.f;
   dst[lane] = v;
 }

@@ -184,7 +184,7 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
 
 // A3/A4 gather: one warp per token.
 __global__ void prop_gather_kernel(const float* __restrict__ cv, const int64_t* __restrict__ seeds,
-                                   int T, int G, int D, int K, float normalizer,
+                                   int T, int G, int D, int K, double normalizer, int extended,
                                    float* __restrict__ cost36, int ld_cost, float* __restrict__ enc32) {
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -200,13 +200,15 @@ __global__ void prop_gather_kernel(const float* __restrict__ cv, const int64_t* 
     }
     cost36[(size_t)t * ld_cost + i] = v;
   }
-  fourier32((float)s, normalizer, enc32 + (size_t)t * 32, lane);
+  // extended: the seed is an integer, its encoding is evaluated in double (exact coordinate, exact power-of-two frequencies)
+  if (extended) fourier32_ext((double)s, normalizer, enc32 + (size_t)t * 32, lane);
+  else fourier32((float)s, (float)normalizer, enc32 + (size_t)t * 32, lane);
 }
 
 // A7 tail: one warp per token: labels = relu(dot(hidden, w) + b + seed)
 __global__ void prop_head_tail_kernel(const float* __restrict__ hidden, const float* __restrict__ w,
                                       const float* __restrict__ b, const int64_t* __restrict__ seeds,
-                                      int T, float* __restrict__ labels) {
+                                      int T, float* __restrict__ labels, float* __restrict__ labels_lo) {
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (t >= T) return;
@@ -215,7 +217,18 @@ __global__ void prop_head_tail_kernel(const float* __restrict__ hidden, const fl
   float s = hv.x * wv.x;
   s = fmaf(hv.y, wv.y, s); s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
   s = warp_sum(s);
-  if (lane == 0) labels[t] = fmaxf(s + b[0] + (float)seeds[t], 0.f);
+  if (lane == 0) {
+    if (labels_lo) {
+      // extended label: the integer seed (up to D-1) plus a small fp32 correction is summed in double and carried as
+      // hi + lo, so that ulp(label) ~ 2e-6 px does not become ~1.5e-3 rad in the 2^14 Fourier frequency downstream
+      const double v = fmax((double)(s + b[0]) + (double)seeds[t], 0.0);
+      const float hi = (float)v;
+      labels[t] = hi;
+      labels_lo[t] = (float)(v - (double)hi);
+    } else {
+      labels[t] = fmaxf(s + b[0] + (float)seeds[t], 0.f);
+    }
+  }
 }
 
 }  // namespace
@@ -232,11 +245,8 @@ int cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int 
   const size_t smem = sizeof(float) * ((featN > hidN ? featN : hidN) + (size_t)TX * G * DP + (size_t)TX * D +
                                        8 * G * 5 + 8 + 16 * 8 * 5 + 16 + 16 * 5 + 4);
   NMRF_REQUIRE(smem <= 227 * 1024, "cost_volume_topk: C=%d D=%d needs %zu B of shared memory", C, D, smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaFuncSetAttribute(cost_volume_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured = smem;
-  }
+  static PerDevice configured;
+  ensure_dynamic_smem(cost_volume_topk_kernel, (int)smem, configured);
   const int tiles_x = (w + TX - 1) / TX;
   cost_volume_topk_kernel<<<B * h * tiles_x, CV_THREADS, smem, stream>>>(f1, f2, h, w, C, G, D, K, eps, *wt,
                                                                        cost_volume, prob, seeds);
@@ -244,22 +254,22 @@ int cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int 
   return check_launch("cost_volume_topk");
 }
 
-int prop_gather(const float* cv, const int64_t* seeds, int P, int G, int D, int K, float normalizer,
+int prop_gather(const float* cv, const int64_t* seeds, int P, int G, int D, int K, double normalizer, int extended,
                 float* cost36, int ld_cost, float* enc32, cudaStream_t stream) {
   NMRF_REQUIRE(cv && seeds && cost36 && enc32, "prop_gather: null pointer");
   NMRF_REQUIRE(ld_cost >= G * 9, "prop_gather: ld_cost=%d < %d", ld_cost, G * 9);
   const int T = P * K;
   const int threads = 256, blocks = (T * 32 + threads - 1) / threads;
-  prop_gather_kernel<<<blocks, threads, 0, stream>>>(cv, seeds, T, G, D, K, normalizer, cost36, ld_cost, enc32);
+  prop_gather_kernel<<<blocks, threads, 0, stream>>>(cv, seeds, T, G, D, K, normalizer, extended, cost36, ld_cost, enc32);
   count_launch();
   return check_launch("prop_gather");
 }
 
 int prop_head_tail(const float* hidden, const float* w, const float* b, const int64_t* seeds, int T,
-                   float* labels, cudaStream_t stream) {
+                   float* labels, float* labels_lo, cudaStream_t stream) {
   NMRF_REQUIRE(hidden && w && b && seeds && labels, "prop_head_tail: null pointer");
   const int threads = 256, blocks = (T * 32 + threads - 1) / threads;
-  prop_head_tail_kernel<<<blocks, threads, 0, stream>>>(hidden, w, b, seeds, T, labels);
+  prop_head_tail_kernel<<<blocks, threads, 0, stream>>>(hidden, w, b, seeds, T, labels, labels_lo);
   count_launch();
   return check_launch("prop_head_tail");
 }

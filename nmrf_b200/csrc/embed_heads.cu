@@ -12,8 +12,9 @@ namespace {
 // its own correlation group (8 consecutive channels = two float4), the 64-ch map a float2.
 __global__ void warp_corr_embed_kernel(const float* __restrict__ f1_cc, const float* __restrict__ f2_cc,
                                        const float* __restrict__ f1_gw, const float* __restrict__ f2_gw,
-                                       const float* __restrict__ labels, int B, int h, int w, int K,
-                                       int Hp, int Wp, int top, int left, float normalizer,
+                                       const float* __restrict__ labels, const float* __restrict__ labels_lo,
+                                       int B, int h, int w, int K,
+                                       int Hp, int Wp, int top, int left, double normalizer,
                                        float* __restrict__ feat, float* __restrict__ enc) {
   const int lane = threadIdx.x & 31;
   const long long tp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -32,10 +33,20 @@ __global__ void warp_corr_embed_kernel(const float* __restrict__ f1_cc, const fl
   }
   const size_t pix = ((size_t)b * h + y) * w + x;
   const float d = labels[pix * K + n];
-  const float xr = (float)x - d;                       // NMP.py:699-702
-  const float xf = floorf(xr);
-  const float a = xr - xf;
-  const int x0 = (int)xf, x1 = x0 + 1;
+  float a;
+  int x0;
+  if (labels_lo) {                                     // extended label hi + lo: sample position and blend weight in double
+    const double xr = (double)x - ((double)d + (double)labels_lo[pix * K + n]);
+    const double xf = floor(xr);
+    a = (float)(xr - xf);
+    x0 = (int)xf;
+  } else {
+    const float xr = (float)x - d;                     // NMP.py:699-702
+    const float xf = floorf(xr);
+    a = xr - xf;
+    x0 = (int)xf;
+  }
+  const int x1 = x0 + 1;
   const bool ok0 = x0 >= 0 && x0 <= w - 1, ok1 = x1 >= 0 && x1 <= w - 1;
   const size_t rowpix = ((size_t)b * h + y) * w;
   const float w0 = 1.f - a, w1 = a;
@@ -64,7 +75,8 @@ __global__ void warp_corr_embed_kernel(const float* __restrict__ f1_cc, const fl
     *reinterpret_cast<float2*>(frow + lane * 2) = c1;
     *reinterpret_cast<float2*>(frow + 64 + lane * 2) = make_float2(t0.x * w0 + t1.x * w1, t0.y * w0 + t1.y * w1);
   }
-  fourier32(d, normalizer, erow, lane);
+  if (labels_lo) fourier32_ext((double)d + (double)labels_lo[pix * K + n], normalizer, erow, lane);
+  else fourier32(d, (float)normalizer, erow, lane);
 }
 
 __global__ void zero_pad_rows_kernel(float* __restrict__ x, int B, int h, int w, int K, int Hp, int Wp,
@@ -80,9 +92,12 @@ __global__ void zero_pad_rows_kernel(float* __restrict__ x, int B, int h, int w,
 }
 
 // One thread per 1/4-resolution pixel: 16 full-resolution sub-pixels, argmax over K, x2, lower median.
+template <typename T>     // T = float (plain) or double (extended labels: label = hi + lo, disp_curr written as hi + lo)
 __global__ void select_median_kernel(const float* __restrict__ delta, const float* __restrict__ score,
-                                     const float* __restrict__ labels, int B, int h, int w, int K,
-                                     int Hp, int Wp, int top, int left, float* __restrict__ disp_curr) {
+                                     const float* __restrict__ labels, const float* __restrict__ labels_lo,
+                                     int B, int h, int w, int K,
+                                     int Hp, int Wp, int top, int left, float* __restrict__ disp_curr,
+                                     float* __restrict__ disp_curr_lo) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int h4 = 2 * h, w4 = 2 * w;
   if (i >= (long long)B * h4 * w4) return;
@@ -90,11 +105,13 @@ __global__ void select_median_kernel(const float* __restrict__ delta, const floa
   const int y = Y >> 1, x = X >> 1, u0 = (Y & 1) * 4, v0 = (X & 1) * 4;
   const size_t pix = ((size_t)b * h + y) * w + x;
   const size_t prow = (((size_t)b * Hp + y + top) * Wp + x + left) * K;
-  float val[16], best[16];
+  T val[16];
+  float best[16];
 #pragma unroll
-  for (int e = 0; e < 16; ++e) { val[e] = 0.f; best[e] = -INFINITY; }
+  for (int e = 0; e < 16; ++e) { val[e] = (T)0; best[e] = -INFINITY; }
   for (int n = 0; n < K; ++n) {
-    const float lab = labels[pix * K + n];
+    T lab = (T)labels[pix * K + n];
+    if (sizeof(T) == 8) lab += (T)labels_lo[pix * K + n];
     const float* dr = delta + (prow + n) * 64;
     const float* sr = score + (prow + n) * 64;
 #pragma unroll
@@ -107,13 +124,14 @@ __global__ void select_median_kernel(const float* __restrict__ delta, const floa
       for (int e = 0; e < 4; ++e) {
         if (sv[e] > best[du * 4 + e]) {              // strict: first maximum wins (torch.max)
           best[du * 4 + e] = sv[e];
-          val[du * 4 + e] = fmaxf(lab + dv[e], 0.f) * 2.f;
+          const T c = lab + (T)dv[e];
+          val[du * 4 + e] = (c > (T)0 ? c : (T)0) * (T)2;
         }
       }
     }
   }
   // lower median of 16 = 8th smallest (torch.median): selection by rank counting
-  float med = val[0];
+  T med = val[0];
 #pragma unroll
   for (int a = 0; a < 16; ++a) {
     int less = 0, eq = 0;
@@ -121,10 +139,13 @@ __global__ void select_median_kernel(const float* __restrict__ delta, const floa
     for (int c = 0; c < 16; ++c) { less += val[c] < val[a]; eq += val[c] == val[a]; }
     if (less <= 7 && 7 < less + eq) med = val[a];
   }
-  disp_curr[i] = med;
+  const float hi = (float)med;
+  disp_curr[i] = hi;
+  if (sizeof(T) == 8) disp_curr_lo[i] = (float)(med - (T)hi);
 }
 
 __global__ void refine_tail_kernel(const float* __restrict__ delta, const float* __restrict__ disp_curr,
+                                   const float* __restrict__ disp_curr_lo,
                                    int B, int h4, int w4, int Hp4, int Wp4, int top, int left, int H, int W,
                                    float* __restrict__ disp_pred, float* __restrict__ disp) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -132,13 +153,19 @@ __global__ void refine_tail_kernel(const float* __restrict__ delta, const float*
   const int X = (int)(i % w4), Y = (int)((i / w4) % h4), b = (int)(i / ((long long)w4 * h4));
   const size_t row = ((size_t)b * Hp4 + Y + top) * Wp4 + X + left;
   const float base = disp_curr[i];
+  const double base_d = disp_curr_lo ? (double)base + (double)disp_curr_lo[i] : 0.0;
   const int Hf = 4 * h4, Wf = 4 * w4;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const float4 d4 = *reinterpret_cast<const float4*>(delta + row * 16 + u * 4);
     float4 o;
-    o.x = fmaxf(base + d4.x, 0.f); o.y = fmaxf(base + d4.y, 0.f);
-    o.z = fmaxf(base + d4.z, 0.f); o.w = fmaxf(base + d4.w, 0.f);
+    if (disp_curr_lo) {
+      o.x = (float)fmax(base_d + (double)d4.x, 0.0); o.y = (float)fmax(base_d + (double)d4.y, 0.0);
+      o.z = (float)fmax(base_d + (double)d4.z, 0.0); o.w = (float)fmax(base_d + (double)d4.w, 0.0);
+    } else {
+      o.x = fmaxf(base + d4.x, 0.f); o.y = fmaxf(base + d4.y, 0.f);
+      o.z = fmaxf(base + d4.z, 0.f); o.w = fmaxf(base + d4.w, 0.f);
+    }
     const int yy = 4 * Y + u, xx = 4 * X;
     *reinterpret_cast<float4*>(disp_pred + ((size_t)b * Hf + yy) * Wf + xx) = o;
     if (yy < H) {
@@ -154,14 +181,14 @@ __global__ void refine_tail_kernel(const float* __restrict__ delta, const float*
 }  // namespace
 
 int warp_corr_embed(const float* f1_cc, const float* f2_cc, const float* f1_gw, const float* f2_gw,
-                    const float* labels, int B, int h, int w, int K, int Hp, int Wp, int top, int left,
-                    float normalizer, float* feat160, float* enc32, cudaStream_t stream) {
+                    const float* labels, const float* labels_lo, int B, int h, int w, int K, int Hp, int Wp, int top, int left,
+                    double normalizer, float* feat160, float* enc32, cudaStream_t stream) {
   NMRF_REQUIRE(f1_cc && f2_cc && f1_gw && f2_gw && labels && feat160 && enc32, "warp_corr_embed: null pointer");
   NMRF_REQUIRE(Hp >= h + top && Wp >= w + left && top >= 0 && left >= 0, "warp_corr_embed: bad padding");
   const long long Tp = (long long)B * Hp * Wp * K;
   const int threads = 256;
   const long long blocks = (Tp * 32 + threads - 1) / threads;
-  warp_corr_embed_kernel<<<(unsigned)blocks, threads, 0, stream>>>(f1_cc, f2_cc, f1_gw, f2_gw, labels, B, h, w, K, Hp, Wp,
+  warp_corr_embed_kernel<<<(unsigned)blocks, threads, 0, stream>>>(f1_cc, f2_cc, f1_gw, f2_gw, labels, labels_lo, B, h, w, K, Hp, Wp,
                                                                    top, left, normalizer, feat160, enc32);
   count_launch();
   return check_launch("warp_corr_embed");
@@ -177,24 +204,30 @@ int zero_pad_rows(float* x, int B, int h, int w, int K, int Hp, int Wp, int top,
   return check_launch("zero_pad_rows");
 }
 
-int select_median(const float* delta, const float* score, const float* labels, int B, int h, int w, int K,
-                  int Hp, int Wp, int top, int left, float* disp_curr, cudaStream_t stream) {
+int select_median(const float* delta, const float* score, const float* labels, const float* labels_lo, int B, int h, int w, int K,
+                  int Hp, int Wp, int top, int left, float* disp_curr, float* disp_curr_lo, cudaStream_t stream) {
   NMRF_REQUIRE(delta && score && labels && disp_curr, "select_median: null pointer");
+  NMRF_REQUIRE((labels_lo == nullptr) == (disp_curr_lo == nullptr), "select_median: labels_lo and disp_curr_lo go together");
   const long long total = (long long)B * 4 * h * w;
   const int threads = 128;
-  select_median_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(delta, score, labels, B, h, w, K,
-                                                                                           Hp, Wp, top, left, disp_curr);
+  const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  if (labels_lo)
+    select_median_kernel<double><<<blocks, threads, 0, stream>>>(delta, score, labels, labels_lo, B, h, w, K, Hp, Wp, top, left,
+                                                                 disp_curr, disp_curr_lo);
+  else
+    select_median_kernel<float><<<blocks, threads, 0, stream>>>(delta, score, labels, nullptr, B, h, w, K, Hp, Wp, top, left,
+                                                                disp_curr, nullptr);
   count_launch();
   return check_launch("select_median");
 }
 
-int refine_tail(const float* delta, const float* disp_curr, int B, int h4, int w4, int Hp4, int Wp4, int top, int left,
+int refine_tail(const float* delta, const float* disp_curr, const float* disp_curr_lo, int B, int h4, int w4, int Hp4, int Wp4, int top, int left,
                 int H, int W, float* disp_pred, float* disp, cudaStream_t stream) {
   NMRF_REQUIRE(delta && disp_curr && disp_pred && disp, "refine_tail: null pointer");
   NMRF_REQUIRE(H <= 4 * h4 && W <= 4 * w4, "refine_tail: output %dx%d larger than padded %dx%d", H, W, 4 * h4, 4 * w4);
   const long long total = (long long)B * h4 * w4;
   const int threads = 128;
-  refine_tail_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(delta, disp_curr, B, h4, w4, Hp4, Wp4,
+  refine_tail_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(delta, disp_curr, disp_curr_lo, B, h4, w4, Hp4, Wp4,
                                                                                          top, left, H, W, disp_pred, disp);
   count_launch();
   return check_launch("refine_tail");

@@ -27,7 +27,7 @@
 //                                 only 2-3 MMAs (tools/probes/seq_probe.cu: 12 MMAs block the issuing thread for 600 of their 768
 //                                 cycles), so whatever one issuer spends between units (two barrier polls, elect, descriptors:
 //                                 ~500 cycles) is tensor idle time unless the other issuer's unit is executing meanwhile.
-// Arithmetic: 3xTF32 with RN hi / exact lo split as in gemm_tc6; LayerNorm two-pass in fp32 from the fp32
+// Arithmetic: 3xTF32 with RN hi / RN lo split as in gemm_tc6; LayerNorm two-pass in fp32 from the fp32
 // accumulator; GELU as gemm_tc6.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -79,10 +79,10 @@ __device__ __forceinline__ void mbar_arrive_m(uint64_t* bar) {
 // optional cycle trace of CTA 0 (debug tooling, nmrf_debug_set_trace; tools/mlp_trace.py): MMA warp: unit g -> g*4 + {0 before the
 // weight wait, 1 after, 2 after issue, 3 after the hand-off barrier (phase 1)}; GELU warp 9: 2048 + chunk*8 + {0 before acc1_full,
 // 1 after, 2 after GELU, 3 after h_free, 4 after stores}; 3968 + tile*8 + {0 p1_full seen, 1 LN done, 2 acc0_final seen, 3 stored}
+#ifdef NMRF_TRACE
 __device__ long long* g_trace_m = nullptr;
-__device__ __forceinline__ void mtrace(long long* tp, int idx) {
-  if (tp && idx < 4096) tp[idx] = clock64();
-}
+#endif
+#define mtrace(tp, idx) NMRF_TRACE_STAMP(tp, idx)
 __device__ __forceinline__ uint32_t idesc_n(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
@@ -114,7 +114,7 @@ __device__ __forceinline__ void ln_worker(MSmem& sm, uint32_t tmem_lane, int q, 
     const float y = (v[i] - mean) * rstd * sm.gamma[k] + sm.beta[k];
     const float h = rna_tf32_fast(y);
     hi[i] = __float_as_uint(h);
-    lo[i] = __float_as_uint(y - h);
+    lo[i] = __float_as_uint(lo_tf32(y, h));
   }
   tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32), hi);
   tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32 + 16), hi + 16);
@@ -153,7 +153,7 @@ __device__ __forceinline__ void gelu_worker(MSmem& sm, uint32_t tmem_lane, uint8
   for (int c2 = 0; c2 < 2; ++c2) {
     float4 h, l;
     h.x = rna_tf32_fast(v[c2 * 4]); h.y = rna_tf32_fast(v[c2 * 4 + 1]); h.z = rna_tf32_fast(v[c2 * 4 + 2]); h.w = rna_tf32_fast(v[c2 * 4 + 3]);
-    l.x = v[c2 * 4] - h.x; l.y = v[c2 * 4 + 1] - h.y; l.z = v[c2 * 4 + 2] - h.z; l.w = v[c2 * 4 + 3] - h.w;
+    l.x = lo_tf32(v[c2 * 4], h.x); l.y = lo_tf32(v[c2 * 4 + 1], h.y); l.z = lo_tf32(v[c2 * 4 + 2], h.z); l.w = lo_tf32(v[c2 * 4 + 3], h.w);
     const uint32_t so = swz(row, j * 2 + c2);
     *reinterpret_cast<float4*>(hi_t + so) = h;
     *reinterpret_cast<float4*>(lo_t + so) = l;
@@ -174,7 +174,11 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
   auto sRaw = [&](int i) { return base + M_OFF_RAW + i * M_TILE; };
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef NMRF_TRACE
   long long* const tp = (blockIdx.x == 0 && (tid == M_MMA_WARP * 32 || tid == M_MMA2_WARP * 32 || tid == M_EPI_WARP0 * 32)) ? g_trace_m : nullptr;
+#else
+  long long* const tp = nullptr;
+#endif
   // phase 1 per tile: n_e k-blocks of E preloaded into acc0 (e_identity: E is the residual, added exactly), then n1 weight
   // units against the k-blocks of X (and of E when it is an ordinary concatenated operand)
   const int n_e = a.e_identity ? a.Ke / M_BK : 0;
@@ -279,7 +283,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
           for (int i = 0; i < 16; ++i) {
             const float h = rna_tf32_fast(vv[i]);
             hi[i] = __float_as_uint(h);
-            lo[i] = __float_as_uint(vv[i] - h);
+            lo[i] = __float_as_uint(lo_tf32(vv[i], h));
           }
           // A buffer j % 4 (TMEM columns of the fc1 accumulators and of LN2(x1), both idle in phase 1): free once the MMAs of
           // the weight unit four back are complete.  The producers wait for the unit THREE back: the `done` barriers rotate
@@ -524,22 +528,16 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
 
 }  // namespace
 
+#ifdef NMRF_TRACE
 int mlp_set_trace(long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_trace_m, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? NMRF_OK : NMRF_ERR_CUDA;
 }
+#endif
 
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream) {
-  static int num_sms = 0;
-  static bool configured = false;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  if (!configured) {
-    cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, M_DYN);
-    configured = true;
-  }
+  const int num_sms = nmrf::num_sms();
+  static PerDevice configured;
+  ensure_dynamic_smem(mlp_chain_kernel, M_DYN, configured);
   const int ntiles = (a.rows + M_BM - 1) / M_BM;
   const int grid = ntiles < num_sms ? ntiles : num_sms;
   mlp_chain_kernel<<<grid, M_BLOCK, M_DYN, stream>>>(a, ntiles);

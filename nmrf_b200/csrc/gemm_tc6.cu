@@ -63,11 +63,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// optional cycle trace of CTA 0 (debug tooling: nmrf_debug_set_trace); slot layout documented in tools/gemm_trace.py
+// optional cycle trace of CTA 0 (debug builds only: make TRACE=1 + nmrf_debug_set_trace); slot layout in tools/gemm_trace.py
+#ifdef NMRF_TRACE
 __device__ long long* g_trace6 = nullptr;
-__device__ __forceinline__ void trace(long long* tp, int idx) {
-  if (tp && idx < 4096) tp[idx] = clock64();
-}
+#endif
+#define trace(tp, idx) NMRF_TRACE_STAMP(tp, idx)
 
 // LayerNorm statistics of 16 rows of a tile (Kx == 128) by one warp: 8 lanes per row (16 floats each, every load
 // instruction covers four rows' contiguous 128 B), four rows per pass, all 16 loads of a lane in flight at once, two
@@ -117,8 +117,10 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
   float* stage_base = reinterpret_cast<float*>(base + (2 * G6_NB + G6_RAW) * G6_TILE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef NMRF_TRACE
   long long* const tp = (blockIdx.x == 0 && (tid == 0 || tid == G6_MMA_WARP * 32 || tid == G6_EPI_WARP0 * 32)) ? g_trace6 : nullptr;
   long long* const tp2 = (blockIdx.x == 0 && tid == 32) ? g_trace6 : nullptr;
+#endif
   const int Ktot = a.Kx + a.Ke;
   const int nkb = (Ktot + G6_BK - 1) / G6_BK;
   const int ntiles = n_rb * n_nc;
@@ -221,7 +223,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
           for (int j = 0; j < 4; ++j) {
             const float h = rna_tf32_fast(vv[j]);
             hi[cc * 4 + j] = __float_as_uint(h);
-            lo[cc * 4 + j] = __float_as_uint(vv[j] - h);     // unrounded: the tensor core truncates, losing <= 2^-25 |x|
+            lo[cc * 4 + j] = __float_as_uint(lo_tf32(vv[j], h));
           }
         }
         trace(tp2, 1024 + unit * 8 + 1);
@@ -403,29 +405,41 @@ int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaSt
   return check_launch("pack_weight_tiles");
 }
 
+#ifdef NMRF_TRACE
 int gemm6_set_trace(long long* dev_ptr) {
   return cudaMemcpyToSymbol(g_trace6, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? NMRF_OK : NMRF_ERR_CUDA;
+}
+#endif
+
+namespace {
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = w[i], h = tc::rna_tf32(x);
+  hi[i] = h;
+  lo[i] = tc::rna_tf32(x - h);
+}
+}  // namespace
+
+int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream) {
+  NMRF_REQUIRE(w && hi && lo && n >= 0, "split_tf32: bad arguments");
+  if (n == 0) return NMRF_OK;
+  split_tf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(w, hi, lo, n);
+  count_launch();
+  return check_launch("split_tf32");
 }
 
 namespace {
 template <int ACT, bool LN>
 void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t stream) {
-  static bool configured = false;     // per instantiation
-  if (!configured) {
-    cudaFuncSetAttribute(token_gemm_tc6_kernel<ACT, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, G6_DYN);
-    configured = true;
-  }
+  static PerDevice configured;        // per instantiation and device
+  ensure_dynamic_smem(token_gemm_tc6_kernel<ACT, LN>, G6_DYN, configured);
   token_gemm_tc6_kernel<ACT, LN><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc);
 }
 }  // namespace
 
-int token_gemm_tc6(const nmrf_gemm_args& a, const float* W_lo, cudaStream_t stream) {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream) {
+  const int num_sms = nmrf::num_sms();
   const int n_rb = (a.rows + G6_BM - 1) / G6_BM;
   const int n_nc = (a.N + G6_BN - 1) / G6_BN;
   const int ntiles = n_rb * n_nc;

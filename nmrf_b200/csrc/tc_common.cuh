@@ -37,6 +37,25 @@ __device__ __forceinline__ float rna_tf32_fast(float x) {
   return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
 }
 
+// Error-compensated 3xTF32 operand split: x = hi + lo, hi = rn_tf32(x), lo = rn_tf32(x - hi).  x - hi is exact in fp32; the
+// tensor core reads only the upper 19 bits of an operand (it TRUNCATES), so an unrounded lo loses up to 2^-10 |lo| ~ 2^-21 |x|
+// per product -- four times the 2^-23 |x| of a rounded lo and enough to raise the rate of flipped argmax / median decisions
+// downstream (truncation split EPE 4.2e-3 px vs 7.6e-6 px for this one).  Two more integer ops per element.
+__device__ __forceinline__ float lo_tf32(float x, float hi) {
+#ifdef NMRF_LO_TRUNC
+  return x - hi;
+#else
+  return rna_tf32_fast(x - hi);
+#endif
+}
+
+// cycle-stamp tracing of CTA 0 (tools/gemm_trace.py, tools/mlp_trace.py): compiled in only with -DNMRF_TRACE (make TRACE=1)
+#ifdef NMRF_TRACE
+#define NMRF_TRACE_STAMP(tp, idx) do { if ((tp) && (idx) < 4096) (tp)[(idx)] = clock64(); } while (0)
+#else
+#define NMRF_TRACE_STAMP(tp, idx) do { } while (0)
+#endif
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

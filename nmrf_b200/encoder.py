@@ -46,7 +46,6 @@ class _Gemm:
     def __init__(self, w2d, bias=None):
         w2d = w2d.detach().float().contiguous()
         self.N, self.K = w2d.shape
-        self.hi, self.lo = _split(w2d)
         ntile = ((self.N + 127) // 128) * ((self.K + 31) // 32)
         self.thi, self.tlo = (torch.empty(ntile * 4096, device=w2d.device) for _ in range(2))
         _lib.check(lib.nmrf_pack_weight_tiles(w2d.data_ptr(), self.N, self.K, self.thi.data_ptr(), self.tlo.data_ptr(),
@@ -59,12 +58,12 @@ class _Gemm:
         a.X, a.ldx, a.Kx = x_ptr, ldx, self.K
         a.E, a.lde, a.Ke, a.ediv = None, 0, 0, 1
         a.ln_gamma, a.ln_beta = None, None
-        a.W, a.ldw = self.hi.data_ptr(), self.hi.stride(0)
+        a.W, a.ldw = self._keep.data_ptr(), self._keep.stride(0)
         a.bias = self.bias.data_ptr() if self.bias is not None else None
         a.R, a.ldr = None, 0
         a.Y, a.ldy = y_ptr, ldy
         a.rows, a.N, a.act = rows, self.N, 0
-        a.W_lo, a.Wt_hi, a.Wt_lo = self.lo.data_ptr(), self.thi.data_ptr(), self.tlo.data_ptr()
+        a.Wt_hi, a.Wt_lo = self.thi.data_ptr(), self.tlo.data_ptr()
         _lib.check(lib.nmrf_token_gemm(ctypes.byref(a), _stream()), "token_gemm")
 
 

@@ -37,6 +37,14 @@ class HotPathConfig:
     num_refine_layers: int = 5
     eps: float = 1e-3                      # DPN.py:51
     tensor_cores: bool = True              # tcgen05 3xTF32 GEMMs (False / NMRF_B200_GEMM=simt: exact-fp32 FMA kernel)
+    # labels / disp_curr carried between stages as hi + lo fp32 pairs summed in double (include/nmrf_b200.h, "Extended
+    # labels"); False reproduces the reference's plain fp32 label arithmetic
+    extended_labels: bool = True
+
+
+def _extended_labels_default():
+    import os
+    return os.environ.get("NMRF_B200_EXT_LABELS", "1") != "0"
 
 
 def _use_mlp_chain_default():
@@ -150,29 +158,23 @@ class _Launches:
     def keep(self, *objs):
         self._keep.extend(objs)
 
-    def split(self, W):
-        """(hi, lo) = nmrf_split_tf32 of an [N, K] weight, K zero-padded to a multiple of 32; cached per tensor"""
+    def tiles(self, W):
+        """hi / lo tile images (nmrf_pack_weight_tiles) of an [N, K] weight for the TMA bulk copies; cached per tensor"""
         key = W.data_ptr()
         if key not in self._splits:
             N, K = W.shape
-            Kp = (K + 31) // 32 * 32
-            Wp = W if Kp == K else torch.nn.functional.pad(W, (0, Kp - K))
-            Wp = Wp.contiguous()
-            hi, lo = torch.empty_like(Wp), torch.empty_like(Wp)
-            st = torch.cuda.current_stream().cuda_stream
-            _lib.check(lib.nmrf_split_tf32(Wp.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wp.numel(), st), "split_tf32")
-            # tile images for the TMA bulk copies of the warp-specialised kernel
-            ntile = ((N + 127) // 128) * (Kp // 32)
+            ntile = ((N + 127) // 128) * ((K + 31) // 32)
             thi, tlo = (torch.empty(ntile * 4096, device=W.device) for _ in range(2))
             Wc = W.contiguous()
+            st = torch.cuda.current_stream(W.device).cuda_stream
             _lib.check(lib.nmrf_pack_weight_tiles(Wc.data_ptr(), N, K, thi.data_ptr(), tlo.data_ptr(), st), "pack_weight_tiles")
-            self._splits[key] = (hi, lo, thi, tlo, W, Wc)
-        return self._splits[key][:4]
+            self._splits[key] = (thi, tlo, W, Wc)
+        return self._splits[key][:2]
 
     def gemm(self, what, X, W, Y, rows, N, *, Kx=None, E=None, Ke=0, ediv=1, ln=None, bias=None, R=None, act=ACT_NONE):
-        W_lo = Wt_hi = Wt_lo = None
+        Wt_hi = Wt_lo = None
         if self.tensor_cores and N % 16 == 0 and N <= 512 and W.is_cuda:
-            W, W_lo, Wt_hi, Wt_lo = self.split(W)
+            Wt_hi, Wt_lo = self.tiles(W)
         a = GemmArgs()
         a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), (Kx if Kx is not None else X.shape[1])
         a.E, a.lde, a.Ke, a.ediv = (E.data_ptr() if E is not None else None), (E.stride(0) if E is not None else 0), Ke, ediv
@@ -182,10 +184,9 @@ class _Launches:
         a.R, a.ldr = (R.data_ptr(), R.stride(0)) if R is not None else (None, 0)
         a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
         a.rows, a.N, a.act = rows, N, act
-        a.W_lo = W_lo.data_ptr() if W_lo is not None else None
         a.Wt_hi = Wt_hi.data_ptr() if Wt_hi is not None else None
         a.Wt_lo = Wt_lo.data_ptr() if Wt_lo is not None else None
-        self.keep(a, X, W, W_lo, Wt_hi, Wt_lo, Y, E, ln, bias, R)
+        self.keep(a, X, W, Wt_hi, Wt_lo, Y, E, ln, bias, R)
         # algorithmic work: 2*MAC flops; activations read+written once (weights are L2-resident, excluded)
         flops = 2.0 * rows * N * (a.Kx + Ke)
         nbytes = 4.0 * (rows * a.Kx + (rows // max(ediv, 1)) * Ke + rows * N * (2 if R is not None else 1))
@@ -223,8 +224,8 @@ class _Launches:
                 _lib.check(rc, what)
 
     def run_timed(self, reps=3):
-        """eager run with a CUDA-event pair around every launch (on the launching stream).
-        Returns [(what, symbol, ms, flops, bytes)] with ms = best of `reps`."""
+        """eager run with a CUDA-event pair around every launch (on the launching stream; call with the plan's device
+        current).  Returns [(what, symbol, ms, flops, bytes)] with ms = best of `reps`."""
         cur = torch.cuda.current_stream()
         stream = cur.cuda_stream
         best = [float("inf")] * len(self.calls)
@@ -249,6 +250,7 @@ class HotPathPlan:
     def __init__(self, pw: PackedWeights, cfg: HotPathConfig, B, C, h8, w8, H, W, device):
         assert h8 * 8 >= H and w8 * 8 >= W
         self.cfg, self.B, self.C, self.h8, self.w8, self.H, self.W = cfg, B, C, h8, w8, H, W
+        self.device = torch.device(device)
         K, G, D = cfg.num_proposals, cfg.cost_group, cfg.max_disp // 8
         h4, w4 = 2 * h8, 2 * w8
         P8, P4 = B * h8 * w8, B * h4 * w4
@@ -275,6 +277,9 @@ class HotPathPlan:
         self.seeds = new(P8, K, dtype=torch.int64)
         self.labels = new(P8, K)
         self.disp_curr = new(B, h4, w4)
+        ext = bool(cfg.extended_labels) and _extended_labels_default()
+        self.labels_lo = new(P8, K) if ext else None           # label = labels + labels_lo (summed in double by the kernels)
+        self.disp_curr_lo = new(B, h4, w4) if ext else None
         self.disp_pred, self.disp = new(B, 4 * h4, 4 * w4), new(B, H, W)
         # ---- workspaces -------------------------------------------------------------------------
         self.x, self.att, self.h1, self.h2 = new(Tmax, 128), new(Tmax, 128), new(Tmax, 128), new(Tmax, 128)
@@ -286,7 +291,8 @@ class HotPathPlan:
         self.launches = _Launches()
         self.launches.tensor_cores = bool(cfg.tensor_cores) and _use_tc_default()
         self.launches.mlp_chain = self.launches.tensor_cores and _use_mlp_chain_default()
-        self._build(pw)
+        with torch.cuda.device(self.device):               # weight packing launches kernels: on the plan's device
+            self._build(pw)
 
     # -------------------------------------------------------------------------------------------
     def _mlp_block(self, L_, T, n2, fc1_w, fc1_b, fc2_w, fc2_b, tag):
@@ -315,7 +321,9 @@ class HotPathPlan:
         L_.add(lib.nmrf_cost_volume_topk, "cost_volume_topk", ptr(self.f1_8), ptr(self.f2_8), B, h8, w8, C, G, D, K,
                c.eps, ctypes.byref(sw), ptr(self.cost_volume), ptr(self.prob), ptr(self.seeds))
         # A3+A4 -------------------------------------------------------------------------------------
-        L_.add(lib.nmrf_prop_gather, "prop_gather", ptr(self.cost_volume), ptr(self.seeds), P8, G, D, K, 3.14 / 64,
+        ext = int(self.labels_lo is not None)
+        optr = lambda t: None if t is None else t.data_ptr()
+        L_.add(lib.nmrf_prop_gather, "prop_gather", ptr(self.cost_volume), ptr(self.seeds), P8, G, D, K, 3.14 / 64, ext,
                ptr(self.cost48), 48, ptr(self.enc))
         L_.gemm("cost_encoder.0", self.cost48, pw.ce0_w, self.h1, T8, 128, bias=pw.ce0_b, act=ACT_GELU)
         L_.gemm("cost_encoder.2", self.h1, pw.ce2_w, self.h2, T8, 128, bias=pw.ce2_b)
@@ -332,10 +340,11 @@ class HotPathPlan:
         (w0, b0), (w1, b1), (w2, b2) = pw.prop_head
         L_.gemm("prop_head.0", self.x, w0, self.h1, T8, 128, ln=pw.prop_norm, bias=b0, act=ACT_RELU)
         L_.gemm("prop_head.1", self.h1, w1, self.h2, T8, 128, bias=b1, act=ACT_RELU)
-        L_.add(lib.nmrf_prop_head_tail, "prop_head.2", ptr(self.h2), ptr(w2), ptr(b2), ptr(self.seeds), T8, ptr(self.labels))
+        L_.add(lib.nmrf_prop_head_tail, "prop_head.2", ptr(self.h2), ptr(w2), ptr(b2), ptr(self.seeds), T8, ptr(self.labels),
+               optr(self.labels_lo))
 
         # A8-A12: inference @1/8 --------------------------------------------------------------------
-        self._stack(L_, pw.stacks["inference"], "inference", self.labels, self.cc8, self.gw8, h8, w8, K,
+        self._stack(L_, pw.stacks["inference"], "inference", self.labels, self.labels_lo, self.cc8, self.gw8, h8, w8, K,
                     g["Hp8"], g["Wp8"], g["top8"], g["left8"], c.window_size, 3.14 / 64, True)
         T8p = g["T8p"]
         (w0, b0), (w1, b1), (w2, b2) = pw.infer_head
@@ -345,12 +354,12 @@ class HotPathPlan:
         L_.gemm("infer_head.2", self.h2, w2, self.delta, T8p, 64, bias=b2)
         # 0.25 * score (NMRF.py:220) does not change the argmax: the exact power-of-two scale is dropped
         L_.gemm("infer_score_head", self.x, pw.score_head[0], self.score, T8p, 64, ln=nrm, bias=pw.score_head[1])
-        L_.add(lib.nmrf_select_median, "select_median", ptr(self.delta), ptr(self.score), ptr(self.labels), B, h8, w8, K,
-               g["Hp8"], g["Wp8"], g["top8"], g["left8"], ptr(self.disp_curr))
+        L_.add(lib.nmrf_select_median, "select_median", ptr(self.delta), ptr(self.score), ptr(self.labels), optr(self.labels_lo),
+               B, h8, w8, K, g["Hp8"], g["Wp8"], g["top8"], g["left8"], ptr(self.disp_curr), optr(self.disp_curr_lo))
 
         # A13: refinement @1/4 ----------------------------------------------------------------------
         h4, w4 = g["h4"], g["w4"]
-        self._stack(L_, pw.stacks["refinement"], "refinement", self.disp_curr, self.cc4, self.gw4, h4, w4, 1,
+        self._stack(L_, pw.stacks["refinement"], "refinement", self.disp_curr, self.disp_curr_lo, self.cc4, self.gw4, h4, w4, 1,
                     g["Hp4"], g["Wp4"], g["top4"], g["left4"], c.refine_window_size, 3.14 / 128, False)
         T4p = g["T4p"]
         (w0, b0), (w1, b1), (w2, b2) = pw.refine_head
@@ -359,15 +368,16 @@ class HotPathPlan:
         L_.gemm("refine_head.1", self.h1, w1, self.h2, T4p, 128, bias=b1, act=ACT_RELU)
         delta16 = self.delta.view(-1)[:T4p * 16].view(T4p, 16)      # dense [T4p,16] as nmrf_refine_tail expects
         L_.gemm("refine_head.2", self.h2, w2, delta16, T4p, 16, bias=b2)
-        L_.add(lib.nmrf_refine_tail, "refine_tail", ptr(delta16), ptr(self.disp_curr), B, h4, w4, g["Hp4"], g["Wp4"],
+        L_.add(lib.nmrf_refine_tail, "refine_tail", ptr(delta16), ptr(self.disp_curr), optr(self.disp_curr_lo), B, h4, w4, g["Hp4"], g["Wp4"],
                g["top4"], g["left4"], self.H, self.W, ptr(self.disp_pred), ptr(self.disp))
 
-    def _stack(self, L_, S, name, labels, cc, gw, h, w, K, Hp, Wp, top, left, ws, normalizer, with_self):
+    def _stack(self, L_, S, name, labels, labels_lo, cc, gw, h, w, K, Hp, Wp, top, left, ws, normalizer, with_self):
         B = self.B
         ptr = lambda t: t.data_ptr()
         Tp = B * Hp * Wp * K
         L_.add(lib.nmrf_warp_corr_embed, name + ".embed", ptr(cc[0]), ptr(cc[1]), ptr(gw[0]), ptr(gw[1]), ptr(labels),
-               B, h, w, K, Hp, Wp, top, left, normalizer, ptr(self.feat), ptr(self.enc))
+               None if labels_lo is None else ptr(labels_lo), B, h, w, K, Hp, Wp, top, left, normalizer, ptr(self.feat),
+               ptr(self.enc))
         L_.gemm(name + ".ffn.fc1", self.feat, S["ffn1_w"], self.h1, Tp, 128, bias=S["ffn1_b"], act=ACT_GELU)
         L_.gemm(name + ".ffn.fc2", self.h1, S["ffn2_w"], self.x, Tp, 128, bias=S["ffn2_b"])
         if Hp != h or Wp != w:
@@ -387,13 +397,19 @@ class HotPathPlan:
 
     # -------------------------------------------------------------------------------------------
     def run(self):
-        """Launch the whole hot path on the current stream (inputs already copied in)."""
-        self.launches.run(torch.cuda.current_stream().cuda_stream)
+        """Launch the whole hot path on the current stream of the plan's device (inputs already copied in).  The device is made
+        current for the launches: the library configures kernels per device and launches on the current one."""
+        with torch.cuda.device(self.device):
+            self.launches.run(torch.cuda.current_stream(self.device).cuda_stream)
 
     def run_with_taps(self):
         """Eager run that clones the stage-boundary tensors (same names as the oracle's taps).  Debug /
         parity tooling only: allocates."""
-        stream = torch.cuda.current_stream().cuda_stream
+        with torch.cuda.device(self.device):
+            return self._run_with_taps()
+
+    def _run_with_taps(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
         g, taps = self.geom, {}
         K = g["K"]
         for fn, what, args in self.launches.calls:

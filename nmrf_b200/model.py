@@ -147,27 +147,28 @@ class DPN(_Params):
         layers = nn.ModuleList(PropagationLayer(prop_embed_dim, context_dim, mlp_ratio) for _ in range(num_prop_layers))
         self.propagation = Propagation(prop_embed_dim, cost_group, layers)
         self.prop_head = MLP(prop_embed_dim, prop_embed_dim, 1, 3)
+        # DPN initialises ITSELF (DPN.py:67-69): its own _init_weights, then the last prop_head layer zeroed
+        self.apply(_init_weights)
+        nn.init.constant_(self.prop_head.layers[-1].weight, 0.0)
+        nn.init.constant_(self.prop_head.layers[-1].bias, 0.0)
 
 
-def init_like_reference(model):
-    """The reference's initialisation (NMRF.py:154-165, DPN.py:90-105): Linear trunc_normal(.02) / zero
-    bias, convs kaiming_normal(fan_out), norms 1/0, RPE tables zero, last prop_head layer zero."""
-    for m in model.modules():
-        if isinstance(m, (nn.Conv1d, nn.Conv2d)):
-            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
-            if isinstance(m, nn.Conv1d) and m.bias is not None:
-                nn.init.constant_(m.bias, 0)
-        elif isinstance(m, nn.Linear):
-            nn.init.trunc_normal_(m.weight, std=0.02)
-            if m.bias is not None:
-                nn.init.constant_(m.bias, 0)
-        elif isinstance(m, nn.LayerNorm):
-            nn.init.constant_(m.weight, 1.0)
+def _init_weights(m):
+    """`_init_weights` of the reference (NMRF.py:154-165, DPN.py:90-105): convs kaiming_normal(fan_out) (Conv1d: zero bias),
+    Linear trunc_normal(.02) / zero bias, LayerNorm / InstanceNorm 1 / 0."""
+    if isinstance(m, (nn.Conv1d, nn.Conv2d)):
+        nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        if isinstance(m, nn.Conv1d) and m.bias is not None:
             nn.init.constant_(m.bias, 0)
-    dpn = getattr(model, "dpn", None)
-    if dpn is not None:
-        nn.init.constant_(dpn.prop_head.layers[-1].weight, 0.0)
-        nn.init.constant_(dpn.prop_head.layers[-1].bias, 0.0)
+    elif isinstance(m, nn.Linear):
+        nn.init.trunc_normal_(m.weight, std=0.02)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+    elif isinstance(m, (nn.LayerNorm, nn.InstanceNorm2d)):
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+        if m.weight is not None:
+            nn.init.constant_(m.weight, 1.0)
 
 
 class NMRF(nn.Module):
@@ -195,6 +196,10 @@ class NMRF(nn.Module):
                                                          for _ in range(num_infer_layers)))
         self.infer_head = MLP(dim, dim, 8 * 8, 3)
         self.infer_score_head = nn.Linear(dim, 8 * 8)
+        # Same order as the reference (NMRF.py:86-87): `apply(_init_weights)` covers only what exists at this point --
+        # concatconv, gw, inference, infer_head, infer_score_head.  The refinement stack keeps torch's default init, DPN has
+        # initialised itself, and a passed-in encoder (e.g. a pretrained Swin backbone) is never touched.
+        self.apply(_init_weights)
         self.refinement = MRFStack(32, dim, nn.ModuleList(RefinementLayer(dim, refine_window_size, mlp_ratio)
                                                           for _ in range(num_refine_layers)))
         self.refine_head = MLP(dim, dim, 4 * 4, 3)
@@ -205,7 +210,6 @@ class NMRF(nn.Module):
         else:
             self.image_encoder = backbone
         self.register_buffer("device_indicator_tensor", torch.empty(0))
-        init_like_reference(self)
         self._packed = None
         self._plans = {}
         self.cudnn_benchmark = False      # let cuDNN autotune the (out-of-path) fp32 convolutions
@@ -270,6 +274,12 @@ class NMRF(nn.Module):
 
     @torch.no_grad()
     def forward_device(self, img1, img2):
+        # everything below launches on the MODEL's device: weight packing, the encoder and the plan make it current
+        # (the library configures its kernels per device and launches on the current one)
+        with torch.cuda.device(self.device):
+            return self._forward_device(img1, img2)
+
+    def _forward_device(self, img1, img2):
         B, _, H, W = img1.shape
         d = self.divis_by                                          # frame_utils.py:264-269 ('proposal' mode)
         pad_h, pad_w = (((H // d) + 1) * d - H) % d, (((W // d) + 1) * d - W) % d
@@ -278,7 +288,8 @@ class NMRF(nn.Module):
             img2 = F.pad(img2, [0, pad_w, 0, pad_h], mode="replicate")
         img1 = img1.contiguous(memory_format=torch.channels_last)
         img2 = img2.contiguous(memory_format=torch.channels_last)
-        if self.fused_encoder and self.compat and self.conv_mode == "3xtf32" and type(self.backbone) is Backbone:
+        if (self.fused_encoder and self.compat and self.conv_mode == "3xtf32" and type(self.backbone) is Backbone
+                and isinstance(self.backbone.norm1, nn.InstanceNorm2d)):      # the fused encoder computes InstanceNorm only
             Hp_, Wp_ = img1.shape[-2:]
             h8, w8 = Hp_ // 8, Wp_ // 8
             plan = self.plan_for(B, self.backbone.output_dim, h8, w8, H, W)
@@ -316,6 +327,10 @@ class NMRF(nn.Module):
         self.forward_device(img1, img2)                                # builds the plan and the encoder
         if self._encoder is None:
             return None
+        with torch.cuda.device(self.device):
+            return self._autotune_encoder(img1, img2)
+
+    def _autotune_encoder(self, img1, img2):
         B, _, H, W = img1.shape
         d = self.divis_by
         pad_h, pad_w = (((H // d) + 1) * d - H) % d, (((W // d) + 1) * d - W) % d

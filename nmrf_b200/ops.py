@@ -28,22 +28,35 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_device(fn):
+    """run `fn` with the device of its first CUDA tensor argument current: libnmrf_b200 launches on the current device
+    and configures its kernels per device, so an operator called on `cuda:1` tensors must not launch on `cuda:0`"""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                with torch.cuda.device(a.device):
+                    return fn(*args, **kwargs)
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def _p(t):
     return None if t is None else t.data_ptr()
 
 
+@_on_device
 def split_tf32(W):
-    """(hi, lo) with hi = rna_tf32(W), lo = rna_tf32(W - hi); the input dimension is zero-padded to a
-    multiple of 32 as the tensor-core GEMM requires."""
+    """(hi, lo) with hi = rna_tf32(W), lo = rna_tf32(W - hi), elementwise (any shape)"""
     _chk(W, "W")
-    N, K = W.shape
-    Kp = (K + 31) // 32 * 32
-    Wp = (W if Kp == K else torch.nn.functional.pad(W, (0, Kp - K))).contiguous()
-    hi, lo = torch.empty_like(Wp), torch.empty_like(Wp)
-    _lib.check(lib.nmrf_split_tf32(Wp.data_ptr(), hi.data_ptr(), lo.data_ptr(), Wp.numel(), _stream()), "split_tf32")
+    hi, lo = torch.empty_like(W), torch.empty_like(W)
+    _lib.check(lib.nmrf_split_tf32(W.data_ptr(), hi.data_ptr(), lo.data_ptr(), W.numel(), _stream()), "split_tf32")
     return hi, lo
 
 
+@_on_device
 def pack_weight_tiles(W):
     """(hi_tiles, lo_tiles): the weight as SWIZZLE_128B tile images for the TMA bulk copies (see nmrf_b200.h)"""
     _chk(W, "W")
@@ -54,10 +67,11 @@ def pack_weight_tiles(W):
     return hi, lo
 
 
-def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, W_lo=None, Wt=None):
+@_on_device
+def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, Wt=None):
     """Y = act(concat(LN?(X), E[r // ediv]) @ W.T + bias) (+ R).  X [rows,Kx], E [*,Ke], W [N,>=Kx+Ke].
-    With W_lo (and W = hi part, both from split_tf32) the tcgen05 3xTF32 kernel is used."""
-    for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R), ("W_lo", W_lo)):
+    With Wt = pack_weight_tiles(W) the tcgen05 3xTF32 kernel is used, otherwise the exact-fp32 FMA kernel."""
+    for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R)):
         _chk(t, n)
     rows, Kx = X.shape
     N = W.shape[0]
@@ -71,12 +85,12 @@ def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=N
     a.R, a.ldr = _p(R), (R.stride(0) if R is not None else 0)
     a.Y, a.ldy = Y.data_ptr(), Y.stride(0)
     a.rows, a.N, a.act = rows, N, act
-    a.W_lo = _p(W_lo)
     a.Wt_hi, a.Wt_lo = (_p(Wt[0]), _p(Wt[1])) if Wt is not None else (None, None)
     _lib.check(lib.nmrf_token_gemm(ctypes.byref(a), _stream()), "token_gemm")
     return Y
 
 
+@_on_device
 def _tile_images(T):
     """T [U,128,32] fp32 (device) -> [U, 8192]: per tile the SWIZZLE_128B image of hi = rna_tf32(T) (4096 floats) followed
     by the image of lo = rna_tf32(T - hi).  Image: the 16-byte chunk c of row r sits at chunk position c ^ (r & 7)."""
@@ -104,6 +118,7 @@ def pack_mlp_stream(W1cat, Wfc1, Wfc2):
     return _tile_images(torch.stack(units, 0))
 
 
+@_on_device
 def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_identity=False):
     """Y = x1 + fc2(GELU(fc1(LN(x1)))) + b_fc2 (bias_out = bias_mid + b_fc2) with x1 = X @ W1.T + bias_mid + E (e_identity: E is the
     residual, added exactly) or x1 = concat(X, E) @ W1cat.T + bias_mid; wstream from pack_mlp_stream(W1 or W1cat, ...).
@@ -127,6 +142,7 @@ def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_ide
     return Y
 
 
+@_on_device
 def cost_volume_topk(f1_nhwc, f2_nhwc, conv_w, D, K, G=4, eps=1e-3):
     """conv_w: dict w0,b0,w1,b1,w2,b2 (dpn.mlp.{0,2,4}).  -> cost_volume [P,G,D], prob [P,D], seeds [P,K] int64"""
     _chk(f1_nhwc, "f1"); _chk(f2_nhwc, "f2")
@@ -145,17 +161,20 @@ def cost_volume_topk(f1_nhwc, f2_nhwc, conv_w, D, K, G=4, eps=1e-3):
     return cv, prob, seeds
 
 
-def prop_gather(cost_volume, seeds, normalizer=3.14 / 64, ld_cost=48):
+@_on_device
+def prop_gather(cost_volume, seeds, normalizer=3.14 / 64, ld_cost=48, extended=True):
+    """extended: Fourier encoding of the (integer) seeds evaluated in double, else in fp32 like the reference"""
     _chk(cost_volume, "cost_volume"); _chk(seeds, "seeds", torch.int64)
     P, G, D = cost_volume.shape
     K = seeds.shape[1]
     cost = torch.empty(P * K, ld_cost, device=seeds.device)
     enc = torch.empty(P * K, 32, device=seeds.device)
-    _lib.check(lib.nmrf_prop_gather(cost_volume.data_ptr(), seeds.data_ptr(), P, G, D, K, normalizer, cost.data_ptr(),
-                                    ld_cost, enc.data_ptr(), _stream()), "prop_gather")
+    _lib.check(lib.nmrf_prop_gather(cost_volume.data_ptr(), seeds.data_ptr(), P, G, D, K, normalizer, int(extended),
+                                    cost.data_ptr(), ld_cost, enc.data_ptr(), _stream()), "prop_gather")
     return cost, enc
 
 
+@_on_device
 def stripe_attention(qkv, B, h, w, K, get_v0, get_v1):
     _chk(qkv, "qkv"); _chk(get_v0, "get_v0"); _chk(get_v1, "get_v1")
     out = torch.empty(qkv.shape[0], 128, device=qkv.device)
@@ -164,35 +183,41 @@ def stripe_attention(qkv, B, h, w, K, get_v0, get_v1):
     return out
 
 
-def prop_head_tail(hidden, w, b, seeds):
+@_on_device
+def prop_head_tail(hidden, w, b, seeds, extended=False):
+    """labels = relu(hidden . w + b + seed).  extended: returns (hi, lo) with label = hi + lo summed in double"""
     _chk(hidden, "hidden"); _chk(w, "w"); _chk(b, "b"); _chk(seeds, "seeds", torch.int64)
     T = hidden.shape[0]
     labels = torch.empty(T, device=hidden.device)
+    lo = torch.empty(T, device=hidden.device) if extended else None
     _lib.check(lib.nmrf_prop_head_tail(hidden.data_ptr(), w.data_ptr(), b.data_ptr(), seeds.data_ptr(), T,
-                                       labels.data_ptr(), _stream()), "prop_head_tail")
-    return labels
+                                       labels.data_ptr(), _p(lo), _stream()), "prop_head_tail")
+    return (labels, lo) if extended else labels
 
 
-def warp_corr_embed(f1_cc, f2_cc, f1_gw, f2_gw, labels, K, Hp, Wp, top, left, normalizer):
-    """NHWC maps [B,h,w,64|256]; labels [B*h*w,K] -> feat [B*Hp*Wp*K,160], enc [.,32] on the padded grid"""
-    for n, t in (("f1_cc", f1_cc), ("f2_cc", f2_cc), ("f1_gw", f1_gw), ("f2_gw", f2_gw), ("labels", labels)):
+@_on_device
+def warp_corr_embed(f1_cc, f2_cc, f1_gw, f2_gw, labels, K, Hp, Wp, top, left, normalizer, labels_lo=None):
+    """NHWC maps [B,h,w,64|256]; labels [B*h*w,K] (+ optional low words) -> feat [B*Hp*Wp*K,160], enc [.,32] on the padded grid"""
+    for n, t in (("f1_cc", f1_cc), ("f2_cc", f2_cc), ("f1_gw", f1_gw), ("f2_gw", f2_gw), ("labels", labels), ("labels_lo", labels_lo)):
         _chk(t, n)
     B, h, w, _ = f1_cc.shape
     Tp = B * Hp * Wp * K
     feat = torch.empty(Tp, 160, device=labels.device)
     enc = torch.empty(Tp, 32, device=labels.device)
     _lib.check(lib.nmrf_warp_corr_embed(f1_cc.data_ptr(), f2_cc.data_ptr(), f1_gw.data_ptr(), f2_gw.data_ptr(),
-                                        labels.data_ptr(), B, h, w, K, Hp, Wp, top, left, normalizer, feat.data_ptr(),
+                                        labels.data_ptr(), _p(labels_lo), B, h, w, K, Hp, Wp, top, left, normalizer, feat.data_ptr(),
                                         enc.data_ptr(), _stream()), "warp_corr_embed")
     return feat, enc
 
 
+@_on_device
 def zero_pad_rows(x, B, h, w, K, Hp, Wp, top, left):
     _chk(x, "x")
     _lib.check(lib.nmrf_zero_pad_rows(x.data_ptr(), B, h, w, K, Hp, Wp, top, left, _stream()), "zero_pad_rows")
     return x
 
 
+@_on_device
 def proposal_attention(qkv, K):
     _chk(qkv, "qkv")
     out = torch.empty(qkv.shape[0], 128, device=qkv.device)
@@ -201,6 +226,7 @@ def proposal_attention(qkv, K):
     return out
 
 
+@_on_device
 def window_attention(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask):
     _chk(qkv, "qkv"); _chk(table, "table")
     out = torch.empty(qkv.shape[0], 128, device=qkv.device)
@@ -209,19 +235,23 @@ def window_attention(qkv, table, B, Hp, Wp, K, ws, shift, self_edge_mask):
     return out
 
 
-def select_median(delta, score, labels, B, h, w, K, Hp, Wp, top, left):
-    _chk(delta, "delta"); _chk(score, "score"); _chk(labels, "labels")
+@_on_device
+def select_median(delta, score, labels, B, h, w, K, Hp, Wp, top, left, labels_lo=None):
+    """-> disp_curr [B,2h,2w]; with labels_lo: (disp_curr, disp_curr_lo), the selection evaluated in double"""
+    _chk(delta, "delta"); _chk(score, "score"); _chk(labels, "labels"); _chk(labels_lo, "labels_lo")
     out = torch.empty(B, 2 * h, 2 * w, device=delta.device)
-    _lib.check(lib.nmrf_select_median(delta.data_ptr(), score.data_ptr(), labels.data_ptr(), B, h, w, K, Hp, Wp, top,
-                                      left, out.data_ptr(), _stream()), "select_median")
-    return out
+    out_lo = torch.empty_like(out) if labels_lo is not None else None
+    _lib.check(lib.nmrf_select_median(delta.data_ptr(), score.data_ptr(), labels.data_ptr(), _p(labels_lo), B, h, w, K, Hp, Wp,
+                                      top, left, out.data_ptr(), _p(out_lo), _stream()), "select_median")
+    return (out, out_lo) if labels_lo is not None else out
 
 
-def refine_tail(delta, disp_curr, Hp4, Wp4, top, left, H, W):
-    _chk(delta, "delta"); _chk(disp_curr, "disp_curr")
+@_on_device
+def refine_tail(delta, disp_curr, Hp4, Wp4, top, left, H, W, disp_curr_lo=None):
+    _chk(delta, "delta"); _chk(disp_curr, "disp_curr"); _chk(disp_curr_lo, "disp_curr_lo")
     B, h4, w4 = disp_curr.shape
     disp_pred = torch.empty(B, 4 * h4, 4 * w4, device=delta.device)
     disp = torch.empty(B, H, W, device=delta.device)
-    _lib.check(lib.nmrf_refine_tail(delta.data_ptr(), disp_curr.data_ptr(), B, h4, w4, Hp4, Wp4, top, left, H, W,
+    _lib.check(lib.nmrf_refine_tail(delta.data_ptr(), disp_curr.data_ptr(), _p(disp_curr_lo), B, h4, w4, Hp4, Wp4, top, left, H, W,
                                     disp_pred.data_ptr(), disp.data_ptr(), _stream()), "refine_tail")
     return disp_pred, disp

@@ -16,6 +16,11 @@ Fixtures
                   (D > w8: the cost-volume edge case; both window pads; odd layer count)
   stages.npz      stress weights, 1x36x68, D=24 K=4 L=2/3/2            inputs+outputs of every stage
   msda.npz        ops/test.py's toy problem (seed 3) + NMRF-shaped cases  vs ms_deform_attn_core_pytorch
+  truth_c1.npz    BASELINE config 2 (SceneFlow 1x540x960, D=24, K=4, L=8/8/8): FLOAT64 oracle disparity + decisions,
+  truth_c1b.npz   the same at the checkpoint-compatible depth 5/5/5,
+  truth_c2.npz    BASELINE config 3 (KITTI 8x375x1248, D=24, K=4, L=8/8/8)
+                  and, as scalars, how far the REAL fp32 reference itself is from that float64 result (EPE, max, flipped
+                  selections): the yardstick the GPU parity tests hold the CUDA path to (`python oracle/make_golden.py truth`)
 Weights are NOT stored (MBs): they are regenerated from the seed by
 nmrf_b200.synthetic.synthetic_state_dict; a fingerprint guards against RNG drift.
 """
@@ -162,9 +167,63 @@ def msda_fixture():
     print("msda fixtures:", [c[0] for c in cases])
 
 
+def truth_fixture(name, B, H, W, cfgd, index):
+    """float64 'truth' for a BASELINE config: the oracle run in float64 (state-dict and images cast; one pair at a time --
+    pairs are independent, InstanceNorm/LayerNorm are per sample), next to the REAL reference in fp32 on the whole batch.
+    The disparity is stored rounded to fp32 (its rounding, <= 6e-6 px, is far below the 1e-3 px bar)."""
+    from oracle import nmrf_oracle as O
+    model, sd = build(cfgd, "reference", seed=0)
+    img1, img2 = synthetic_pair(B, H, W, cfgd["max_disp"], index)
+    ref = run(model, img1, img2, canonical=True)                       # the real reference, fp32, whole batch
+    sd64 = O.to_float64(sd)
+    mk = lambda: O.OracleConfig(max_disp=cfgd["max_disp"], num_proposals=cfgd["K"], num_prop_layers=cfgd["L"][0],
+                                num_infer_layers=cfgd["L"][1], num_refine_layers=cfgd["L"][2], taps={})
+    disp64, sel64, seeds64, lab64, sel32 = [], [], [], [], []
+    for b in range(B):
+        c64 = mk()
+        o64 = O.forward(sd64, c64, img1[b:b + 1], img2[b:b + 1])
+        disp64.append(o64["disp"]); sel64.append(c64.taps["sel"]); seeds64.append(c64.taps["seeds"]); lab64.append(c64.taps["labels"])
+        c32 = mk()
+        O.forward(sd, c32, img1[b:b + 1], img2[b:b + 1])
+        sel32.append(c32.taps["sel"])
+        del c64, c32
+    disp64, sel64, seeds64 = torch.cat(disp64), torch.cat(sel64), torch.cat(seeds64)
+    lab64, sel32 = torch.cat(lab64), torch.cat(sel32)
+    d = (ref["disp"].double() - disp64).abs()
+    per_pair = d.flatten(1).mean(1)
+    seeds_ref = ref["initial_proposal"].reshape(-1, cfgd["K"]).long()
+    np.savez_compressed(
+        os.path.join(OUT, name),
+        B=B, H=H, W=W, max_disp=cfgd["max_disp"], K=cfgd["K"], L=np.array(cfgd["L"]), index=index, weight_seed=0,
+        fingerprint=state_dict_fingerprint(sd),
+        disp64=npy(disp64.float()), sel64=npy(sel64).astype(np.uint8), seeds64=npy(seeds64).astype(np.uint8),
+        proposal64=npy(lab64.float()),
+        ref32_epe=float(d.mean()), ref32_max=float(d.max()), ref32_epe_per_pair=npy(per_pair),
+        ref32_frac_gt_1e3=float((d > 1e-3).double().mean()),
+        ref32_seed_rows_identical=float((seeds_ref == seeds64).all(-1).double().mean()),
+        oracle32_selection_flips=int((sel32 != sel64).sum()), n_selections=int(sel64.numel()),
+        ref32_proposal_epe=float((ref["proposal"].reshape(-1, cfgd["K"]).double() - lab64).abs().mean()),
+        threads=torch.get_num_threads())
+    print(name, "real fp32 reference vs float64 oracle: EPE %.3e max %.3f px, >1e-3 px: %.2e of pixels, seeds identical %.6f, "
+          "fp32-oracle selection flips %d / %d" % (float(d.mean()), float(d.max()), float((d > 1e-3).double().mean()),
+                                                   float((seeds_ref == seeds64).all(-1).double().mean()),
+                                                   int((sel32 != sel64).sum()), sel64.numel()), flush=True)
+
+
+TRUTH = {
+    "truth_c1": (1, 540, 960, dict(max_disp=192, K=4, L=(8, 8, 8)), 0),
+    "truth_c1b": (1, 540, 960, dict(max_disp=192, K=4, L=(5, 5, 5)), 0),
+    "truth_c2": (8, 375, 1248, dict(max_disp=192, K=4, L=(8, 8, 8)), 0),
+}
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "truth":
+        for name in (sys.argv[2:] or list(TRUTH)):
+            truth_fixture(name, *TRUTH[name])
+        sys.exit(0)
     e2e_fixture("e2e_tiny", 1, 96, 160, dict(max_disp=64, K=2, L=(2, 2, 2)), 0)
     e2e_fixture("e2e_small", 2, 75, 150, dict(max_disp=192, K=4, L=(3, 3, 3)), 3)
     stages_fixture()

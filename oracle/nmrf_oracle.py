@@ -71,7 +71,7 @@ def _timm_mlp(sd, prefix, x):
 
 def fourier_embed(c, normalizer):
     """NMP.py:35-51 with N_freqs=15, logscale: [sin(c' 2^i) (15), cos(c' 2^i) (15), c']."""
-    freq = 2 ** torch.linspace(0, 14, 15)
+    freq = 2 ** torch.linspace(0, 14, 15, dtype=c.dtype, device=c.device)
     cs = (c * normalizer).unsqueeze(-1)
     f = cs * freq
     return torch.cat([f.sin(), f.cos(), cs], dim=-1)
@@ -155,7 +155,7 @@ def sample_cost(cv, seeds):
     """NMP.py:618-634: cost[p,n,g*9+(o+4)] = cv[p,g,clamp(seed+o,0,D-1)]."""
     P, G, D = cv.shape
     K = seeds.shape[1]
-    off = torch.arange(-4, 5)
+    off = torch.arange(-4, 5, device=seeds.device)
     idx = (seeds[..., None] + off).clamp(0, D - 1)                 # [P,K,9]
     g = cv[:, None, :, :].expand(P, K, G, D).gather(3, idx[:, :, None, :].expand(P, K, G, 9))
     return g.reshape(P, K, G * 9)
@@ -175,9 +175,9 @@ def stripe_attention(sd, prefix, q, k, v, vertical):
     split = lambda t: t.reshape(B, Wn, L * K, 2, 32).permute(0, 1, 3, 2, 4)   # [B,Wn,2,L*K,32]
     qh, kh, vh = split(q) * (32 ** -0.5), split(k), split(v)
     attn = qh @ kh.transpose(-2, -1)
-    pix = torch.arange(L).repeat_interleave(K)
+    pix = torch.arange(L, device=q.device).repeat_interleave(K)
     same = pix[:, None] == pix[None, :]
-    mask = torch.zeros(L * K, L * K)
+    mask = torch.zeros(L * K, L * K, dtype=q.dtype, device=q.device)
     mask[same] = float("-inf")
     mask.fill_diagonal_(0.0)                            # NMP.py:203-208
     attn = F.softmax(attn + mask, dim=-1)
@@ -215,7 +215,7 @@ def propagation(sd, cfg, cv, seeds, context, B, h, w):
     p = "dpn.propagation"
     cost = sample_cost(cv, seeds)
     cf = _lin(sd, p + ".cost_encoder.2", F.gelu(_lin(sd, p + ".cost_encoder.0", cost)))
-    seeds_f = seeds.float()
+    seeds_f = seeds.to(cv.dtype)
     enc = fourier_embed(seeds_f, 3.14 / 64)
     x = F.linear(torch.cat([cf, enc], dim=-1), sd[p + ".proj.weight"])
     if cfg.taps is not None:
@@ -237,7 +237,7 @@ def warp_sample(fmap, labels):
     [0,w-1] (grid_sample bilinear/zeros/align_corners=True, NMP.py:695-706).
     labels [B,h,w,K] -> [B,h,w,K,C]."""
     B, C, h, w = fmap.shape
-    xs = torch.arange(w, dtype=torch.float32).view(1, 1, w, 1)
+    xs = torch.arange(w, dtype=labels.dtype, device=labels.device).view(1, 1, w, 1)
     xr = xs - labels
     x0 = torch.floor(xr)
     a = xr - x0
@@ -286,20 +286,20 @@ def basic_attention(sd, p, x, enc):
 # --------------------------------------------------------------------------------------
 # A11  (shifted-)window attention with contextual RPE   (NMP.py:241-289, 343-364, 195-239)
 # --------------------------------------------------------------------------------------
-def _window_index(Hp, Wp, ws, shift):
+def _window_index(Hp, Wp, ws, shift, device=None):
     """Token-grid index of every window slot, shift done by indexing instead of roll
     (NMP.py:249-250: rolled[yr] = orig[(yr+shift) % Hp]); plus Swin region ids in rolled
     coordinates (NMP.py:221-232)."""
-    yr = torch.arange(Hp)
-    xr = torch.arange(Wp)
+    yr = torch.arange(Hp, device=device)
+    xr = torch.arange(Wp, device=device)
     yo, xo = (yr + shift) % Hp, (xr + shift) % Wp
     lin = (yo[:, None] * Wp + xo[None, :])                          # [Hp,Wp] rolled -> original linear idx
     win = lin.reshape(Hp // ws, ws, Wp // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
     if shift > 0:
-        band = lambda n: (torch.arange(n) >= n - ws).long() + (torch.arange(n) >= n - shift).long()
+        band = lambda n: (torch.arange(n, device=device) >= n - ws).long() + (torch.arange(n, device=device) >= n - shift).long()
         reg = band(Hp)[:, None] * 3 + band(Wp)[None, :]
     else:
-        reg = torch.zeros(Hp, Wp, dtype=torch.long)
+        reg = torch.zeros(Hp, Wp, dtype=torch.long, device=device)
     reg = reg.reshape(Hp // ws, ws, Wp // ws, ws).permute(0, 2, 1, 3).reshape(-1, ws * ws)
     return win, reg
 
@@ -308,13 +308,14 @@ def window_attention(sd, p, qkv, B, Hp, Wp, K, ws, shift, self_edge_mask):
     """qkv [B,Hp,Wp,K,384] -> [B,Hp,Wp,K,128]."""
     nh = 4
     Pn = ws * ws
-    win, reg = _window_index(Hp, Wp, ws, shift)                     # [Wn,Pn]
+    dev = qkv.device
+    win, reg = _window_index(Hp, Wp, ws, shift, dev)                # [Wn,Pn]
     Wn = win.shape[0]
     flat = qkv.reshape(B, Hp * Wp, K, 3, nh, 32)
     g = flat[:, win.reshape(-1)].reshape(B, Wn, Pn, K, 3, nh, 32)
     q, k, v = g[..., 0, :, :], g[..., 1, :, :], g[..., 2, :, :]     # [B,Wn,Pn,K,nh,32]
     table = sd[p + ".relative_position_enc_table"]                  # [(2ws-1)^2, 384]
-    cy, cx = torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")
+    cy, cx = torch.meshgrid(torch.arange(ws, device=dev), torch.arange(ws, device=dev), indexing="ij")
     cy, cx = cy.reshape(-1), cx.reshape(-1)
     rel = (cy[:, None] - cy[None, :] + ws - 1) * (2 * ws - 1) + (cx[:, None] - cx[None, :] + ws - 1)
     rpe = table[rel.reshape(-1)].reshape(Pn, Pn, nh, 96)            # NMP.py:257-260
@@ -325,13 +326,13 @@ def window_attention(sd, p, qkv, B, Hp, Wp, K, ws, shift, self_edge_mask):
     qr = torch.einsum("bwpnhc,pqhc->bwhpnq", qs, Rk)
     kr = torch.einsum("bwqmhc,pqhc->bwhpqm", k, Rq * s)
     logits = qk + qr[..., None] + kr[:, :, :, :, None, :, :]
-    mask = torch.zeros(Wn, Pn, K, Pn, K)
+    mask = torch.zeros(Wn, Pn, K, Pn, K, dtype=qkv.dtype, device=dev)
     if shift > 0:
         diff = reg[:, :, None] != reg[:, None, :]                   # [Wn,Pn,Pn]
         mask = mask.masked_fill(diff[:, :, None, :, None], float("-inf"))
     if self_edge_mask:
-        eyeP = torch.eye(Pn, dtype=torch.bool)[:, None, :, None]
-        eyeK = torch.eye(K, dtype=torch.bool)[None, :, None, :]
+        eyeP = torch.eye(Pn, dtype=torch.bool, device=dev)[:, None, :, None]
+        eyeK = torch.eye(K, dtype=torch.bool, device=dev)[None, :, None, :]
         mask = mask.masked_fill((eyeP & ~eyeK)[None], float("-inf"))
     logits = logits + mask[None, :, None]
     A = F.softmax(logits.reshape(B, Wn, nh, Pn, K, Pn * K), dim=-1).reshape(logits.shape)
@@ -440,18 +441,28 @@ def hot_path(sd, cfg, f1_list, f2_list):
     return {
         "proposal": labels.reshape(B, -1, K),
         "prob": prob,
-        "initial_proposal": seeds.float().reshape(B, -1, K),
+        "initial_proposal": seeds.to(prob.dtype).reshape(B, -1, K),
         "disp_pred": disp_pred,
         "disp_padded": disp_pred * 4,
     }
 
 
+def to_float64(sd, device=None):
+    """state-dict with every floating-point tensor cast to float64 (integer buffers untouched), optionally moved to `device`.
+    The oracle is device-agnostic torch code: on a CUDA device (fp64, no TF32 involved) it serves the GPU tests as a fast
+    float64 truth for stage-level comparisons."""
+    return {k: (v.double() if v.dtype.is_floating_point else v).to(device or v.device) for k, v in sd.items()}
+
+
 @torch.no_grad()
 def forward(sd, cfg, img1, img2):
-    """NMRF.forward(sample) on CPU: images [B,3,H,W] in 0..255 -> output dict."""
+    """NMRF.forward(sample) on CPU: images [B,3,H,W] in 0..255 -> output dict.
+    Arithmetic type = the state-dict's: fp32 restates the reference; a state-dict cast with
+    `to_float64` gives the float64 "truth" the parity tests measure both implementations against."""
     H, W = img1.shape[-2:]
-    img1, _ = pad_images(img1.float(), cfg.divis_by)
-    img2, _ = pad_images(img2.float(), cfg.divis_by)
+    w0 = sd[cfg.backbone_prefix + ".conv1.weight"]
+    img1, _ = pad_images(img1.to(w0.device, w0.dtype), cfg.divis_by)
+    img2, _ = pad_images(img2.to(w0.device, w0.dtype), cfg.divis_by)
     feats = backbone_resnet(sd, cfg.backbone_prefix, torch.cat([img1, img2], 0))
     f4a, f4b = feats[0].chunk(2, 0)
     f8a, f8b = feats[1].chunk(2, 0)

@@ -38,7 +38,7 @@ def test_binding_matches_header():
 
 def test_helpers_work_without_a_gpu():
     from nmrf_b200 import _lib
-    assert _lib.lib.nmrf_abi_version() == _lib.ABI_VERSION == 6
+    assert _lib.lib.nmrf_abi_version() == _lib.ABI_VERSION == 7
     assert isinstance(_lib.launch_count(), int)
     # argument validation happens before any CUDA call: a bad GEMM is rejected with a message
     a = _lib.GemmArgs()
@@ -51,7 +51,7 @@ def test_struct_layout_matches_c():
     from nmrf_b200 import _lib
     assert ctypes.sizeof(_lib.SeedWeights) == 6 * 8
     # X,ldx,Kx | E,lde,Ke,ediv | g,b | W,ldw | bias | R,ldr | Y,ldy | rows,N,act
-    assert ctypes.sizeof(_lib.GemmArgs) == 144
+    assert ctypes.sizeof(_lib.GemmArgs) == 136
     # X,ldx,Kx | E,lde,Ke | Wstream | bias_mid | g,b | b1 | bias_out | Y,ldy,rows | e_identity (+pad)
     assert ctypes.sizeof(_lib.MlpArgs) == 104
 

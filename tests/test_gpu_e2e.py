@@ -1,15 +1,16 @@
 """GPU: the whole drop-in model (`nmrf_b200.NMRF`, public API, host tensors in) against
   (a) the committed outputs of the REAL reference (tests/golden/e2e_*.npz),
-  (b) the CPU oracle on the same seeded inputs, at sizes the oracle finishes in seconds,
-  (c) size-independent properties at the benchmark's full size (540x960, D=24, K=4).
+  (b) FLOAT64 truth (the oracle in float64) on the same seeded inputs, with the fp32 reference arithmetic as the yardstick,
+  (c) the three BASELINE configurations (540x960 8/8/8, 540x960 5/5/5, KITTI 8x375x1248 8/8/8) through the committed
+      float64 fixtures tests/golden/truth_*.npz, which also record how far the REAL fp32 reference is from that truth.
 Tolerance (BASELINE.json north_star): EPE <= 1e-3 px in fp32; integer seed path exact modulo ties.
 
-How the 1e-3 bar is applied: at init-scale weights the reference's own discrete decisions (argmax
-over K, NMRF.py:228; top-K seeds) are near-tied, so ANY fp32 re-ordering flips ~0.01 % of them and a flip moves a
-pixel by whole pixels -- the CPU oracle against itself with 1e-7 relative input noise already shows EPE 2e-5..2e-3.
-The tests therefore assert (1) every stage boundary agrees to ~1e-5 relative, (2) decisions agree (seeds except
-numerical ties; selections >= 99.9 %), (3) EPE <= 1e-3 px on all pixels not adjacent to a flipped decision (>= 85 % of
-the image), (4) the overall EPE stays within the oracle's own conditioning (<= 2e-2 px).
+How the 1e-3 bar is applied.  At init-scale weights a handful of the reference's own discrete decisions
+(argmax over K, NMRF.py:228; the 4x4 lower median, :231) are numerically tied: ANY fp32 rounding pattern flips some of
+them, and one flipped median block moves 16 pixels by whole pixels -- the real fp32 reference is itself 2.6e-4 ... 3.1e-3 px
+(EPE) away from the float64 evaluation of its own formulas, by exactly that mechanism.  The CUDA path is therefore held to
+        EPE(cuda, float64) <= max(1e-3, 1.25 * EPE(fp32 reference, float64))     on ALL pixels, no mask,
+with seeds identical, and every stage boundary within a small multiple of the fp32 reference's own distance from float64.
 """
 import pytest
 import torch
@@ -23,17 +24,20 @@ EPE_BAR = 1e-3
 
 
 def assert_parity(m):
-    stage = {k: v for k, v in m["rel_err"].items() if not k.startswith("refinement")}
-    assert max(stage.values()) <= 2e-4, m["rel_err"]
-    # refinement tokens sit downstream of the discrete selection: even away from flips they see them through L layers
-    # of (shifted) window attention, so they are held to a looser intermediate bound; the decisive check is the EPE below
-    assert max(v for k, v in m["rel_err"].items() if k.startswith("refinement")) <= 5e-3, m["rel_err"]
-    assert m["abs_err_prob"] <= 1e-5
-    assert m["seed_rows_identical"] >= 0.98 and m["seed_value_gap_max"] <= 2e-6, m
-    assert m["selection_agreement"] >= 0.999, m
-    assert m["frac_px_away_from_flips"] >= 0.5 and m["EPE_away_from_flips"] <= EPE_BAR, m   # (small images: few blocks)
-    assert m["disp_curr_abs_err_max_on_agreeing_blocks"] <= 1e-3, m
-    assert m["EPE"] <= 2e-2, m
+    c, r = m["cuda"], m["ref32"]
+    # (1) the headline: end-point error against float64 truth, all pixels, relative to the fp32 reference's own
+    assert c["EPE"] <= max(EPE_BAR, 1.25 * r["EPE"]), (c, r)
+    # (2) integer paths: seeds identical to the truth (a different pick can only be a numerically tied entry)
+    assert c["seed_rows_identical"] >= 0.999 and c["seed_value_gap_max"] <= 2e-6, c
+    assert c["prob_abs_err"] <= 1e-5 and c["proposal_EPE"] <= 1e-5, c
+    # (3) flipped argmax-over-K selections: no more than the fp32 reference arithmetic flips itself (+ Poisson slack)
+    assert c["selection_flips"] <= 2 * r["selection_flips"] + 12, (c["selection_flips"], r["selection_flips"])
+    # (4) every stage boundary: noise level (rms) within 4x of the fp32 reference arithmetic's own distance from float64
+    for k, v in m["stage"].items():
+        if v["cuda"] is None or v["ref32"] is None:
+            continue
+        assert v["cuda"]["rms"] <= max(4.0 * v["ref32"]["rms"], 2e-6), (k, v)
+        assert v["cuda"]["max"] <= 2e-4 or k.startswith("refinement"), (k, v)
 
 
 def _seed_mismatch_is_tie(out_seeds, ref_seeds, prob_nms, K):
@@ -60,11 +64,12 @@ def test_against_reference_golden(name):
     frac = _seed_mismatch_is_tie(out["initial_proposal"], T(g["initial_proposal"]), cfg.taps["prob_nms"], int(g["K"]))
     assert frac <= 0.02
     assert float((out["prob"].cpu() - T(g["prob"])).abs().max()) <= 1e-5
-    # the reference's outputs directly: overall EPE within the conditioning bound, the bulk of the pixels within the bar
+    # the real reference's fp32 outputs directly: the bulk of the pixels within the bar, the mean within what two fp32
+    # evaluations of near-tied decisions can differ by (each is ~1e-3 px from float64, see the module docstring)
     d = (out["disp"].cpu() - T(g["disp"])).abs()
-    assert float(d.mean()) <= 2e-2 and float(d.median()) <= 1e-4, (float(d.mean()), float(d.median()))
-    assert float((d <= EPE_BAR).float().mean()) >= 0.85
-    assert epe(out["proposal"].cpu(), T(g["proposal"])) <= EPE_BAR
+    assert float(d.mean()) <= 1e-2 and float(d.median()) <= 1e-4, (float(d.mean()), float(d.median()))
+    assert float((d <= EPE_BAR).float().mean()) >= 0.95
+    assert epe(out["proposal"].cpu(), T(g["proposal"])) <= 1e-5
     m, _, _ = parity_metrics(model, sd, int(g["max_disp"]), int(g["K"]), g["L"], T(g["img1"]), T(g["img2"]))
     assert_parity(m)
 
@@ -75,14 +80,42 @@ def test_against_reference_golden(name):
     (1, 270, 480, 192, 4, (5, 5, 5)),     # checkpoint-compatible depth at half the benchmark size
     (2, 375, 1248, 192, 4, (1, 1, 1)),    # KITTI geometry (BASELINE config 2): 375 -> 376 rows, 47 x 156 grid padded to 48 x 156
 ])
-def test_against_oracle(B, H, W, max_disp, K, L):
+def test_against_float64_truth(B, H, W, max_disp, K, L):
     model, sd = build_product_model(max_disp, K, L, 0, "reference")
     model = model.cuda()
     img1, img2 = synthetic_pair(B, H, W, max_disp, index=2)
     m, out, ref = parity_metrics(model, sd, max_disp, K, L, img1, img2)
-    print(m)
+    print({k: m[k] for k in ("cuda", "ref32")})
     assert_parity(m)
-    assert m["proposal_EPE"] <= EPE_BAR
+
+
+@pytest.mark.parametrize("name", ["truth_c1", "truth_c1b", "truth_c2"])
+def test_baseline_configs_against_float64_fixture(name):
+    """BASELINE configs 2 (540x960, 8/8/8 and the checkpoint depth 5/5/5) and 3 (KITTI, batch 8) at FULL size: the committed
+    float64 disparity (oracle/make_golden.py truth) and the real fp32 reference's own distance from it."""
+    g = golden(name)
+    B, H, W, K, L, md = int(g["B"]), int(g["H"]), int(g["W"]), int(g["K"]), g["L"], int(g["max_disp"])
+    model, sd = build_product_model(md, K, L, int(g["weight_seed"]), "reference")
+    check_fingerprint(sd, g["fingerprint"])
+    model = model.cuda()
+    img1, img2 = synthetic_pair(B, H, W, md, index=int(g["index"]))
+    out = model({"img1": img1, "img2": img2})
+    d = (out["disp"].double().cpu() - T(g["disp64"]).double()).abs()
+    bar = max(EPE_BAR, 1.25 * float(g["ref32_epe"]))
+    print(name, "EPE vs float64 %.3e (max %.2f px); real fp32 reference %.3e (max %.2f px); bar %.3e"
+          % (float(d.mean()), float(d.max()), float(g["ref32_epe"]), float(g["ref32_max"]), bar))
+    assert float(d.mean()) <= bar                                            # all pixels, no mask
+    seeds = out["initial_proposal"].long().reshape(-1, K).cpu()
+    assert float((seeds == T(g["seeds64"]).long()).all(-1).double().mean()) >= 0.9999
+    assert float((out["proposal"].double().cpu().reshape(-1, K) - T(g["proposal64"]).double()).abs().mean()) <= 1e-5
+    # flipped selections against the float64 decisions, next to what the fp32 oracle flips itself
+    plan = next(iter(model._plans.values()))
+    gm, h8, w8 = plan.geom, plan.h8, plan.w8
+    sc = plan.score[:gm["T8p"]].reshape(B, gm["Hp8"], gm["Wp8"], K, 64)[:, gm["top8"]:gm["top8"] + h8, gm["left8"]:gm["left8"] + w8]
+    sel = sc.reshape(B, h8, w8, K, 8, 8).permute(0, 1, 4, 2, 5, 3).reshape(B, h8 * 8, w8 * 8, K).argmax(-1).cpu()
+    flips = int((sel != T(g["sel64"]).long()).sum())
+    print(name, "selection flips vs float64:", flips, "fp32 oracle:", int(g["oracle32_selection_flips"]))
+    assert flips <= 2 * int(g["oracle32_selection_flips"]) + 12
 
 
 def test_stage_chain_with_stress_weights():
@@ -148,6 +181,28 @@ def test_full_size_properties():
     assert float(dd.median()) <= 1e-4 and float(dd.mean()) <= 2e-2
     m, _, _ = parity_metrics(model, sd, max_disp, K, L, img1, img2)
     assert_parity(m)
+
+
+def test_plain_fp32_labels_mode_matches_fp32_oracle_labels():
+    """HotPathConfig.extended_labels = False (NMRF_B200_EXT_LABELS=0): the reference's plain fp32 label arithmetic; the
+    default extended mode must return the same fp32 `proposal` words."""
+    import os
+    max_disp, K, L = 96, 3, (1, 1, 1)
+    model, sd = build_product_model(max_disp, K, L, 0, "reference")
+    model = model.cuda()
+    img1, img2 = synthetic_pair(1, 120, 200, max_disp, index=1)
+    a = model({"img1": img1, "img2": img2})
+    os.environ["NMRF_B200_EXT_LABELS"] = "0"
+    try:
+        model.invalidate()
+        b = model({"img1": img1, "img2": img2})
+        assert next(iter(model._plans.values())).labels_lo is None
+    finally:
+        del os.environ["NMRF_B200_EXT_LABELS"]
+        model.invalidate()
+    assert torch.equal(a["proposal"], b["proposal"]) and torch.equal(a["initial_proposal"], b["initial_proposal"])
+    d = (a["disp"] - b["disp"]).abs()
+    assert float(d.median()) <= 1e-4
 
 
 def test_no_cpu_path_and_eval_only():

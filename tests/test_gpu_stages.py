@@ -63,9 +63,8 @@ def test_token_gemm(ops, rows, Kx, Ke, ediv, N, ln, act, res, tc):
     ref = torch.relu(ref) if act == 1 else torch.nn.functional.gelu(ref) if act == 2 else ref
     if res:
         ref = ref + R.double()
-    Wd, W_lo = (ops.split_tf32(cuda(W)) if tc else (cuda(W), None))
     Wt = ops.pack_weight_tiles(cuda(W)) if tc else None
-    out = ops.token_gemm(cuda(X), Wd, E=cuda(E) if Ke else None, ediv=ediv, W_lo=W_lo, Wt=Wt,
+    out = ops.token_gemm(cuda(X), cuda(W), E=cuda(E) if Ke else None, ediv=ediv, Wt=Wt,
                          ln=(cuda(gam), cuda(bet)) if ln else None, bias=cuda(b), R=cuda(R) if res else None, act=act)
     assert rel_err(out, ref) <= (4e-6 if tc else 2e-6)
 
@@ -82,10 +81,10 @@ def test_token_gemm_tc_many_tiles_and_split_exactness(ops):
     X = torch.randn(rows, 128, generator=g)
     E = torch.randn(rows, 32, generator=g)
     ref = torch.cat([X, E], 1).double() @ W.double().T
-    out = ops.token_gemm(cuda(X), hi, E=cuda(E), W_lo=lo, Wt=ops.pack_weight_tiles(cuda(W)))
+    out = ops.token_gemm(cuda(X), cuda(W), E=cuda(E), Wt=ops.pack_weight_tiles(cuda(W)))
     assert rel_err(out, ref) <= 4e-6
-    out5 = ops.token_gemm(cuda(X), hi, E=cuda(E), W_lo=lo)          # without tile images: the smem-A schedule
-    assert rel_err(out5, ref) <= 4e-6
+    out_fma = ops.token_gemm(cuda(X), cuda(W), E=cuda(E))           # without tile images: the exact-fp32 FMA kernel
+    assert rel_err(out_fma, ref) <= 2e-6
 
 
 def test_token_gemm_residual_in_place(ops):
@@ -195,12 +194,18 @@ def test_prop_gather(ops):
     P, G, D, K = 200, 4, 24, 4
     cv = torch.randn(P, G, D, generator=g)
     seeds = torch.randint(0, D, (P, K), generator=g)
-    cost, enc = ops.prop_gather(cuda(cv), cuda(seeds))
+    cost, enc = ops.prop_gather(cuda(cv), cuda(seeds), extended=False)
     assert torch.equal(cost.cpu()[:, :36], O.sample_cost(cv, seeds).reshape(P * K, 36))     # pure gather: exact
     assert float(cost[:, 36:].abs().max()) == 0.0
-    ref = O.fourier_embed(seeds.float().reshape(-1), 3.14 / 64)
+    ref = O.fourier_embed(seeds.float().reshape(-1), 3.14 / 64)            # the reference's fp32 arithmetic
     assert float((enc.cpu()[:, :31] - ref).abs().max()) <= 1e-6
     assert float(enc[:, 31].abs().max()) == 0.0
+    # extended: the encoding of the integer seed evaluated in double -> held to the float64 oracle (fp32 storage rounding only)
+    cost2, enc2 = ops.prop_gather(cuda(cv), cuda(seeds), extended=True)
+    assert torch.equal(cost2, cost)
+    ref64 = O.fourier_embed(seeds.double().reshape(-1), 3.14 / 64)
+    assert float((enc2.cpu()[:, :31].double() - ref64).abs().max()) <= 6e-8
+    assert float((ref.double() - ref64).abs().max()) >= 1e-5              # ... which the fp32 evaluation misses by this much
 
 
 def test_prop_head_tail(ops):
@@ -210,6 +215,13 @@ def test_prop_head_tail(ops):
     ref = torch.relu(hid.double() @ w.double() + b.double() + seeds.double())
     out = ops.prop_head_tail(cuda(hid), cuda(w), cuda(b), cuda(seeds))
     assert rel_err(out, ref) <= 2e-6
+    hi, lo = ops.prop_head_tail(cuda(hid), cuda(w), cuda(b), cuda(seeds), extended=True)
+    assert torch.equal(hi, out) or rel_err(hi, ref) <= 2e-6                 # the hi word is the fp32 label
+    # hi + lo carries the sum seed + (fp32 dot + bias) without rounding it to fp32 again
+    s32 = (hid.double() @ w.double() + b.double()).float().double()         # what an exact fp32 dot would hold (~1e-6 off ours)
+    ext = hi.cpu().double() + lo.cpu().double()
+    assert float((ext - torch.relu(s32 + seeds.double())).abs().max()) <= 2e-5
+    assert float(lo.abs().max()) <= 2e-6 * 24
 
 
 @pytest.fixture(params=[1, 0], ids=["tcgen05", "fma"])
@@ -325,6 +337,73 @@ def test_refine_tail(ops):
     disp_pred, disp = ops.refine_tail(cuda(dpad), cuda(dc), Hp, Wp, top, left, H, W)
     assert torch.equal(disp_pred.cpu(), pred)
     assert torch.equal(disp.cpu(), (pred * 4)[:, :H, :W])
+
+
+# ---- extended labels (label = hi + lo, include/nmrf_b200.h): held to FLOAT64 evaluations of the same formulas ----
+def _split_hi_lo(x64):
+    hi = x64.float()
+    return hi, (x64 - hi.double()).float()
+
+
+def test_warp_corr_embed_extended_labels(ops):
+    from nmrf_b200.hotpath import center_pad
+    g = torch.Generator().manual_seed(31)
+    B, h, w, K, ws, norm = 1, 7, 40, 4, 6, 3.14 / 64
+    cc1, cc2 = torch.randn(B, 64, h, w, generator=g), torch.randn(B, 64, h, w, generator=g)
+    gw1, gw2 = torch.randn(B, 256, h, w, generator=g), torch.randn(B, 256, h, w, generator=g)
+    lab64 = torch.rand(B, h, w, K, generator=g, dtype=torch.float64) * (w + 4) - 2
+    hi, lo = _split_hi_lo(lab64)
+    Hp, top = center_pad(h, ws)
+    Wp, left = center_pad(w, ws)
+    nh = lambda t: cuda(t.permute(0, 2, 3, 1))
+    feat, enc = ops.warp_corr_embed(nh(cc1), nh(cc2), nh(gw1), nh(gw2), cuda(hi.reshape(-1, K)), K, Hp, Wp, top, left, norm,
+                                    labels_lo=cuda(lo.reshape(-1, K)))
+    d = lambda t: t.double()
+    wg = O.warp_sample(d(gw2), lab64)
+    corr = (d(gw1).permute(0, 2, 3, 1)[:, :, :, None, :] * wg).reshape(B, h, w, K, 32, 8).mean(-1)
+    ref = torch.cat([d(cc1).permute(0, 2, 3, 1)[:, :, :, None, :].expand(B, h, w, K, 64), O.warp_sample(d(cc2), lab64), corr], -1)
+    inner = feat.cpu().reshape(B, Hp, Wp, K, 160)[:, top:top + h, left:left + w]
+    assert rel_err(inner, ref) <= 1e-6
+    ref_enc = O.fourier_embed(lab64, norm)
+    got = enc.cpu().reshape(B, Hp, Wp, K, 32)[:, top:top + h, left:left + w, :, :31]
+    assert float((got.double() - ref_enc).abs().max()) <= 1e-7         # fp32 storage rounding only, at every frequency
+    # the plain fp32 path (labels_lo = NULL) cannot do that: one ulp of the label is ~1e-3 rad at 2^14
+    _, enc32 = ops.warp_corr_embed(nh(cc1), nh(cc2), nh(gw1), nh(gw2), cuda(hi.reshape(-1, K)), K, Hp, Wp, top, left, norm)
+    got32 = enc32.cpu().reshape(B, Hp, Wp, K, 32)[:, top:top + h, left:left + w, :, :31]
+    assert float((got32.double() - ref_enc).abs().max()) >= 1e-4
+
+
+def test_select_median_and_refine_tail_extended(ops):
+    from nmrf_b200.hotpath import center_pad
+    g = torch.Generator().manual_seed(77)
+    B, h, w, K, ws = 1, 7, 13, 4, 6
+    Hp, top = center_pad(h, ws)
+    Wp, left = center_pad(w, ws)
+    P = B * h * w
+    delta, score = torch.randn(P, K, 64, generator=g) * 3, torch.randn(P, K, 64, generator=g)
+    lab64 = torch.rand(P, K, generator=g, dtype=torch.float64) * 20
+    hi, lo = _split_hi_lo(lab64)
+    coarse = torch.relu(lab64[..., None] + delta.double())
+    unshuf = lambda t: t.reshape(B, h, w, K, 8, 8).permute(0, 1, 4, 2, 5, 3).reshape(B, h * 8, w * 8, K)
+    _, idx = torch.max(unshuf(score), -1, keepdim=True)
+    d = torch.gather(unshuf(coarse), -1, idx).squeeze(-1) * 2
+    ref = torch.median(d.reshape(B, h * 2, 4, w * 2, 4).permute(0, 1, 3, 2, 4).reshape(B, h * 2, w * 2, 16), -1)[0]
+    pad = lambda t: torch.nn.functional.pad(t.reshape(B, h, w, K, 64), (0, 0, 0, 0, left, Wp - w - left, top, Hp - h - top),
+                                            value=float("nan")).reshape(-1, 64)
+    dc, dc_lo = ops.select_median(cuda(pad(delta)), cuda(pad(score)), cuda(hi), B, h, w, K, Hp, Wp, top, left, labels_lo=cuda(lo))
+    ext = dc.cpu().double() + dc_lo.cpu().double()
+    assert float((ext - ref).abs().max()) <= 1e-12                    # the double sum, carried exactly as hi + lo
+    assert torch.equal(dc.cpu(), ref.float())
+    # refine tail on the extended disp_curr
+    h4, w4, H, W = 2 * h, 2 * w, 8 * h - 3, 8 * w - 5
+    Hp4, top4 = center_pad(h4, 4)
+    Wp4, left4 = center_pad(w4, 4)
+    dl = torch.randn(B, h4, w4, 16, generator=g) * 3
+    pred = torch.relu(ref[..., None] + dl.double()).reshape(B, h4, w4, 4, 4).permute(0, 1, 3, 2, 4).reshape(B, h4 * 4, w4 * 4)
+    dpad = torch.nn.functional.pad(dl, (0, 0, left4, Wp4 - w4 - left4, top4, Hp4 - h4 - top4), value=float("nan")).reshape(-1, 16)
+    disp_pred, disp = ops.refine_tail(cuda(dpad), dc, Hp4, Wp4, top4, left4, H, W, disp_curr_lo=dc_lo)
+    assert torch.equal(disp_pred.cpu(), pred.float())                   # correctly rounded double sums
+    assert torch.equal(disp.cpu(), (pred.float() * 4)[:, :H, :W])
 
 
 # ---------------------------------------------------------------------------------------------

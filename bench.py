@@ -216,8 +216,7 @@ def main():
     w = WORKLOAD
     B, H, W, K, steps, warmup = w["B"], w["H"], w["W"], w["K"], args.steps, max(args.warmup, 3)
     model, sd = build_model(dev)
-    tune = tuple(t.to(dev) for t in synthetic_pair(B, H, W, w["max_disp"], 9999))
-    runner = GraphedNMRF(model, B, H, W, autotune_convs=True, tune_images=tune)
+    runner = GraphedNMRF(model, B, H, W)
     plan = runner.plan
     # distinct pairs per rank (weak scaling: every rank processes its own pairs)
     host = [tuple(t.pin_memory() for t in synthetic_pair(B, H, W, w["max_disp"], rank * N_PAIRS + i)) for i in range(N_PAIRS)]
@@ -329,7 +328,6 @@ def main():
                        "step": "one pass of the hot path (SURVEY.md §8(a) A1-A13: cost volume ... disparity, "
                                f"{launches_per_step} libnmrf_b200 kernels in one CUDA graph) over feature maps resident in HBM",
                        "l2": "flushed between timed steps (256 MiB memset)", "cuda_graph": True,
-                       "cudnn_autotune": runner.autotune_report,
                        "gemm": "tcgen05 3xTF32" if plan.launches.tensor_cores else "fp32 FMA"},
             "full_forward": {"value": pairs_total / t_dev_max, "unit": "pairs/s", "ms_per_step": 1e3 * t_dev_max / steps,
                              "includes": "torch feature extractor + conv heads (cuDNN, 3xTF32-exact) + hot path, one CUDA graph, "

@@ -80,17 +80,20 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
  * hi_tiles / lo_tiles must hold ceil(N/128)*ceil(K/32)*4096 floats each. */
 int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float* lo_tiles, void* stream);
 /* ---- fused block tail: proj + residual + LayerNorm + Mlp in ONE launch ----------------------------
- *   x1 = X[r, 0:Kx] . W1^T + bias_mid + E[r, 0:128]                  (e_identity = 1; SwinNMP / CSWinNMP: x + proj(attn),
- *                                                                    NMP.py:358-359, 570-571: E is the residual stream x, which is
- *                                                                    loaded into the fp32 accumulator before the MMAs, i.e. added exactly)
+ *   x1 = E[r, 0:128] + (X[r, 0:Kx] . W1^T + bias_mid)                (e_identity = 1; SwinNMP / CSWinNMP: x + proj(attn),
+ *                                                                    NMP.py:358-359, 570-571: E is the residual stream x; it is
+ *                                                                    held in fp32 registers and added with round-to-nearest
+ *                                                                    adds, never inside a tensor-core accumulator)
  *   x1 = concat(X[r, 0:Kx], E[r, 0:Ke]) . W1cat^T + bias_mid         (e_identity = 0: E is an ordinary concatenated operand)
- *   Y  = x1 + fc2( GELU( fc1( LN(x1) ) ) ) + b_fc2                   (x + Mlp(norm2(x)), NMP.py:362-363,572-573; timm Mlp 128->512->128)
+ *   Y  = x1 + (fc2( GELU( fc1( LN(x1) ) ) ) + bias_out)              (x + Mlp(norm2(x)), NMP.py:362-363,572-573; timm Mlp 128->512->128;
+ *                                                                    bias_out = the fc2 bias)
  * Wstream: n1 + 32 units of 8192 floats, n1 = Kx/32 (e_identity) or (Kx+Ke)/32 (16 KB hi image + 16 KB lo image, SWIZZLE_128B
  * shared-memory images of [128 x 32] fp32 tiles):  P1(0..n1-1), then F1(c) at n1 + c, then F2(c) at n1 + 16 + c (c = hidden chunk
  * of 32, 0..15; every CTA walks the k-blocks and the chunks starting from its own rotation, so the fp32 summation order differs
  * per tile):  P1(j)[n,k] = W1[n, 32j+k];  F1(c)[r,k] = Wfc1[32c + r%32, 32(r/32) + k];  F2(c)[n,k] = Wfc2[n, 32c+k]
- * (nmrf_b200/ops.py: pack_mlp_stream).  bias_out = bias_mid + b_fc2.  Kx and Ke must be multiples of 32, Kx + Ke <= 512;
- * Y may alias E (each tile is read completely before it is written).  Same 3xTF32 arithmetic as nmrf_token_gemm. */
+ * (nmrf_b200/ops.py: pack_mlp_stream).  Kx and Ke must be multiples of 32, Kx + Ke <= 512; Y may alias E (every element
+ * is read and later written by the same thread).  Same 3xTF32 arithmetic as nmrf_token_gemm; the fc2 accumulator is drained
+ * into the registers every four hidden chunks (at most 48 MMAs ever accumulate into the same tensor-memory columns). */
 typedef struct {
   const float* X; int ldx; int Kx;
   const float* E; int lde; int Ke;             /* may be NULL (Ke = 0) */
@@ -98,10 +101,10 @@ typedef struct {
   const float* bias_mid;                       /* [128] */
   const float* ln_gamma; const float* ln_beta; /* [128] */
   const float* b1;                             /* [512] fc1 bias */
-  const float* bias_out;                       /* [128] */
+  const float* bias_out;                       /* [128] fc2 bias */
   float* Y; int ldy;
   int rows;
-  int e_identity;                              /* 1: E [rows,128] is the residual, added exactly (not part of the weight stream) */
+  int e_identity;                              /* 1: E [rows,128] is the residual, added in fp32 registers (not part of the weight stream) */
 } nmrf_mlp_args;
 int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream);
 
@@ -233,28 +236,63 @@ int nmrf_ms_deform_attn_forward_dev(const float* value, const int64_t* spatial_s
                                     int N, int S, int M, int Dh, int L, int Lq, int P,
                                     float* out, void* stream);
 
+/* ---- N1 / N2 (next rows of the scope table): k x k convolution over an NHWC image on tcgen05 ------------------------------
+ * replaces nn.Conv2d in the reference's Backbone and conv heads (nmrf/models/backbone.py:16-98, NMRF.py:56-65,
+ * DPN.py:45-49): Y[n, yo, xo, :] = bias + sum_{ky, kx, c} X[n, yo*stride - pad + ky, xo*stride - pad + kx, c] * W[:, ky, kx, c]
+ * (zero padding), as an implicit GEMM on the token-GEMM kernel: GEMM row = output pixel, k = (ky*kw + kx)*Cin + c, the A
+ * tile of a (tap, 32-channel block) gathered with zero-filled cp.async straight from X -- no im2col buffer, no hi/lo copy of
+ * the activations (the operand split happens in the producer warps).  Same error-compensated 3xTF32 arithmetic and the
+ * same grouped accumulation as nmrf_token_gemm, so a K = 9 * 256 convolution is as accurate as an fp32 one.
+ * X is addressed by strides (floats): img_stride between samples, row_stride between rows, pix_stride between pixels; the Cin
+ * floats of a tap are contiguous, Cin % 32 == 0, all strides multiples of 4.  (The 7x7 / 3-channel stem runs on the same
+ * kernel over a zero-bordered 4-channel image: one "tap" per kernel row = 8 pixels x 4 floats, see nmrf_image_prep.)
+ * Wt_hi / Wt_lo: nmrf_pack_weight_tiles of the weight reshaped to [Cout, kh*kw*Cin] (tap-major).  Y: [N, Ho, Wo, Cout]
+ * contiguous; Ho / Wo = 0 derive them from the usual formula.  Cout % 16 == 0. */
+typedef struct {
+  const float* X; int N; int H; int W;
+  int64_t img_stride; int row_stride; int pix_stride;
+  int Cin; int kh; int kw; int stride; int pad;
+  const float* Wt_hi; const float* Wt_lo;
+  const float* bias;                           /* [Cout] or NULL */
+  float* Y; int Cout; int Ho; int Wo;
+} nmrf_conv_args;
+int nmrf_conv2d(const nmrf_conv_args* c, void* stream);
+
 /* ---- N2 (next row of the scope table): element-wise glue of the convolutional feature extractor, NHWC ----
  * replaces nn.InstanceNorm2d + ReLU + residual add between the convolutions of the reference's Backbone /
- * conv heads (nmrf/models/backbone.py:13-45, NMRF.py:56-65, DPN.py:45-49) and prepares the next convolution's
- * error-compensated operand.  All tensors NHWC ([N, H*W, C], C % 4 == 0).
+ * conv heads (nmrf/models/backbone.py:13-45, NMRF.py:56-65, DPN.py:45-49).  All tensors NHWC ([N, H*W, C], C % 4 == 0).
  *   stats [N, C, 2] doubles, ZEROED by the caller: sum and sum of squares over H*W (biased variance, eps 1e-5).
- *   apply:  y = IN(x) if x_stats else x;  relu if relu_inner;  y += (IN(r) if r_stats else r) if r;  relu if relu_outer;
- *           out_plain [N,HW,C] (or NULL) = y;  out_cat3 [N,HW,3C] (or NULL) = [hi | lo | hi] with hi = rn_tf32(y),
- *           lo = rn_tf32(y - hi): convolving it with weights [w_hi | w_hi | w_lo] (input-channel concatenation) is
- *           x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, i.e. 3xTF32 in one library call.
+ *   apply:  y = IN(x) if x_stats else x;  relu if relu_inner;  y += (IN(r) if r_stats else r) if r;  relu if relu_outer;  out = y
  */
 int nmrf_instnorm_stats(const float* x, int N, int HW, int C, double* stats, void* stream);
 int nmrf_instnorm_apply(const float* x, const double* x_stats, const float* r, const double* r_stats,
-                        int N, int HW, int C, int relu_inner, int relu_outer,
-                        float* out_plain, float* out_cat3, void* stream);
-/* x [rows, C] -> out [rows, 3C] = [hi | lo | hi] */
-int nmrf_split_cat3(const float* x, int64_t rows, int C, float* out, void* stream);
-/* left / right images [B,H,W,3] (the channels_last storage of [B,3,H,W]), values 0..255 -> [2B,H,W,9] = [hi | lo | hi] of
- * 2 (x / 255) - 1 (nmrf/models/backbone.py:86): normalisation + batching + operand split of the stem convolution in one pass */
-int nmrf_image_prep(const float* img1_nhwc, const float* img2_nhwc, int B, int H, int W, float* out_cat3, void* stream);
+                        int N, int HW, int C, int relu_inner, int relu_outer, float* out, void* stream);
+/* N3 prologue in one pass: left / right images [B,3,H,W], values 0..255, in ANY layout (element strides of the batch,
+ * channel, row and column dimensions: NCHW = (3HW, HW, W, 1), channels_last = (3HW, 1, 3W, 3)) -> out [2B, Hp+6, Wp+8, 4]:
+ * 2 (x / 255) - 1 (nmrf/models/backbone.py:86) of the image replicate-padded on the right / bottom to Hp x Wp (InputPadder
+ * mode 'proposal', nmrf/utils/frame_utils.py:264-275), stored as RGB0 pixels inside a ZERO border of 3 pixels (left / top)
+ * and 5 / 3 pixels (right / bottom) -- the zero padding of the 7x7 stride-2 stem convolution, materialised so that the stem is
+ * one nmrf_conv2d with kh = 7, kw = 1, Cin = 32 (8 pixels x 4 floats per kernel row, 16-byte aligned), stride 2. */
+int nmrf_image_prep(const float* img1, const float* img2, int B, int H, int W, int Hp, int Wp,
+                    int64_t stride_b, int64_t stride_c, int64_t stride_y, int64_t stride_x, float* out_rgb0, void* stream);
 /* 2x2 average pool of an NHWC map [N,h,w,C] (backbone.py:96-98; h, w even are used, odd tails dropped like avg_pool2d):
- * plain result split by sample half (out_a: samples 0..N/2-1, out_b: the rest) and its [hi | lo | hi] operand [N,h/2,w/2,3C] */
-int nmrf_avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_cat3, void* stream);
+ * the result split by sample half (out_a: samples 0..N/2-1 = left images, out_b: the rest) and, optionally (out_all != NULL),
+ * once more as one [N,h/2,w/2,C] tensor (the operand of the conv heads at 1/8 resolution) */
+int nmrf_avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_all, void* stream);
+
+/* ---- N4 (next row): what every pipeline of the reference does with the disparity ------------------------------------
+ * Disparity metrics of DispEvaluator.process (nmrf/utils/evaluation.py:345-359), reduced on the device: per image b,
+ *   acc[b][0] = number of valid pixels (gt < max_disp, and valid_gt != 0 when valid_gt is given: `only_valid`),
+ *   acc[b][1] = sum of |pr - gt| over them,   acc[b][2] = number of D1 outliers  (e > 3) & (e / gt > 0.05),
+ *   acc[b][3 + i] = number of pixels with e > thresholds[i]  ("bad tau").
+ * acc: [B, 3 + n_thres] doubles, ZEROED by the caller (the kernel accumulates: calls over batches may share it);
+ * thresholds is a HOST array (n_thres <= 8).  The reference's per-image means are acc[b][k] / acc[b][0]; an image without
+ * valid pixels is skipped by the reference (NaN check, evaluation.py:349-350). */
+int nmrf_disp_metrics(const float* disp_pr, const float* disp_gt, const uint8_t* valid_gt /* or NULL */, int B, int64_t HW,
+                      float max_disp, const float* thresholds_host, int n_thres, double* acc, void* stream);
+/* KITTI 16-bit disparity encoding of writeDispKITTI (nmrf/utils/frame_utils.py:237-239): out = uint16(round(disp * 256)),
+ * round half to even like np.round; n values. */
+int nmrf_disp_to_kitti_u16(const float* disp, int64_t n, uint16_t* out, void* stream);
 
 #ifdef __cplusplus
 }

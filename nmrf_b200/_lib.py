@@ -44,6 +44,18 @@ class MlpArgs(Structure):
     ]
 
 
+class ConvArgs(Structure):
+    """mirror of nmrf_conv_args"""
+    _fields_ = [
+        ("X", c_void_p), ("N", c_int), ("H", c_int), ("W", c_int),
+        ("img_stride", c_int64), ("row_stride", c_int), ("pix_stride", c_int),
+        ("Cin", c_int), ("kh", c_int), ("kw", c_int), ("stride", c_int), ("pad", c_int),
+        ("Wt_hi", c_void_p), ("Wt_lo", c_void_p),
+        ("bias", c_void_p),
+        ("Y", c_void_p), ("Cout", c_int), ("Ho", c_int), ("Wo", c_int),
+    ]
+
+
 class SeedWeights(Structure):
     """mirror of nmrf_seed_weights"""
     _fields_ = [("w0", c_void_p), ("b0", c_void_p), ("w1", c_void_p), ("b1", c_void_p),
@@ -55,11 +67,11 @@ _I, _F, _D, _P = c_int, c_float, c_double, c_void_p
 SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
     "nmrf_mlp_chain": [POINTER(MlpArgs), _P],
+    "nmrf_conv2d": [POINTER(ConvArgs), _P],
     "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
     "nmrf_instnorm_stats": [_P, _I, _I, _I, _P, _P],
-    "nmrf_instnorm_apply": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P],
-    "nmrf_split_cat3": [_P, c_int64, _I, _P, _P],
-    "nmrf_image_prep": [_P, _P, _I, _I, _I, _P, _P],
+    "nmrf_instnorm_apply": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "nmrf_image_prep": [_P, _P, _I, _I, _I, _I, _I, c_int64, c_int64, c_int64, c_int64, _P, _P],
     "nmrf_avgpool2_split": [_P, _I, _I, _I, _I, _P, _P, _P, _P],
     "nmrf_set_attention_impl": [_I],
     "nmrf_debug_set_trace": [_P],
@@ -74,6 +86,8 @@ SIGNATURES = {
     "nmrf_window_attention": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "nmrf_select_median": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "nmrf_refine_tail": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
+    "nmrf_disp_metrics": [_P, _P, _P, _I, c_int64, _F, POINTER(c_float), _I, _P, _P],
+    "nmrf_disp_to_kitti_u16": [_P, c_int64, _P, _P],
     "nmrf_ms_deform_attn_forward": [_P, POINTER(c_int64), POINTER(c_int64), _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
     "nmrf_ms_deform_attn_forward_dev": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
 }
@@ -84,18 +98,40 @@ if not os.path.exists(LIB_PATH):
         f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
         "or `make -C nmrf_b200/csrc`. nmrf_b200 has no CPU/PyTorch fallback.")
 
-lib = ctypes.CDLL(LIB_PATH)
-for _name, _args in SIGNATURES.items():
-    _fn = getattr(lib, _name)
-    _fn.argtypes = _args
-    _fn.restype = c_int
-for _name, (_res, _args) in HELPERS.items():
-    _fn = getattr(lib, _name)
-    _fn.argtypes = _args
-    _fn.restype = _res
 
-if lib.nmrf_abi_version() != ABI_VERSION:
-    raise ImportError(f"libnmrf_b200.so ABI {lib.nmrf_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
+class _Library:
+    """The shared library, dlopen'ed at FIRST USE (its presence is checked at import, above).  Code that only needs the
+    parameter containers or the synthetic generators -- bench.py's `--impl reference` arm, the CPU tests of the host logic --
+    therefore never maps libnmrf_b200.so into its process; every compute entry point still fails loudly without it."""
+
+    def __init__(self):
+        self._cdll = None
+
+    def _load(self):
+        cdll = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(cdll, name)
+            fn.argtypes = args
+            fn.restype = c_int
+        for name, (res, args) in HELPERS.items():
+            fn = getattr(cdll, name)
+            fn.argtypes = args
+            fn.restype = res
+        if cdll.nmrf_abi_version() != ABI_VERSION:
+            raise ImportError(f"libnmrf_b200.so ABI {cdll.nmrf_abi_version()} != binding ABI {ABI_VERSION}: rebuild")
+        self._cdll = cdll
+        return cdll
+
+    @property
+    def loaded(self):
+        return self._cdll is not None
+
+    def __getattr__(self, name):
+        cdll = self.__dict__.get("_cdll") or self._load()
+        return getattr(cdll, name)
+
+
+lib = _Library()
 
 
 def check(rc, what):

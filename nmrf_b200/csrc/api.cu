@@ -39,6 +39,7 @@ int check_launch(const char* what) {
 
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
 int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream);
+int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
 int mlp_set_trace(long long* dev_ptr);
@@ -54,9 +55,8 @@ int stripe_attention(const float*, int, int, int, int, const float*, const float
 int stripe_attention_tc(const float*, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 bool window_attention_mma_supported(int K, int ws);
 int instnorm_stats(const float*, int, int, int, double*, cudaStream_t);
-int instnorm_apply(const float*, const double*, const float*, const double*, int, int, int, int, int, float*, float*, cudaStream_t);
-int split_cat3(const float*, long long, int, float*, cudaStream_t);
-int image_prep(const float*, const float*, int, int, int, float*, cudaStream_t);
+int instnorm_apply(const float*, const double*, const float*, const double*, int, int, int, int, int, float*, cudaStream_t);
+int image_prep(const float*, const float*, int, int, int, int, int, long long, long long, long long, long long, float*, cudaStream_t);
 int avgpool2_split(const float*, int, int, int, int, float*, float*, float*, cudaStream_t);
 int window_attention_mma(const float*, const float*, int, int, int, int, int, int, int, float*, cudaStream_t);
 int warp_corr_embed(const float*, const float*, const float*, const float*, const float*, const float*, int, int, int, int, int,
@@ -65,6 +65,8 @@ int zero_pad_rows(float*, int, int, int, int, int, int, int, int, cudaStream_t);
 int select_median(const float*, const float*, const float*, const float*, int, int, int, int, int, int, int, int, float*, float*,
                   cudaStream_t);
 int refine_tail(const float*, const float*, const float*, int, int, int, int, int, int, int, int, int, float*, float*, cudaStream_t);
+int disp_metrics(const float*, const float*, const uint8_t*, int, long long, float, const float*, int, double*, cudaStream_t);
+int disp_to_kitti_u16(const float*, long long, uint16_t*, cudaStream_t);
 int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const float*, const float*, int, int, int, int,
                            int, int, int, float*, bool, cudaStream_t);
 
@@ -122,6 +124,10 @@ int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream) {
   NMRF_REQUIRE(a->ldx % 4 == 0 && a->ldy % 4 == 0 && (a->Ke == 0 || a->lde % 4 == 0), "mlp_chain: bad leading dimension");
   if (a->rows == 0) return NMRF_OK;
   return mlp_chain(*a, ST(stream));
+}
+int nmrf_conv2d(const nmrf_conv_args* c, void* stream) {
+  NMRF_REQUIRE(c != nullptr, "conv2d: null argument struct");
+  return conv2d_tc6(*c, ST(stream));
 }
 int nmrf_set_attention_impl(int tensor_cores) {
   g_attn_tc.store(tensor_cores ? 1 : 0, std::memory_order_relaxed);
@@ -192,14 +198,12 @@ int nmrf_instnorm_stats(const float* x, int N, int HW, int C, double* stats, voi
   return instnorm_stats(x, N, HW, C, stats, ST(stream));
 }
 int nmrf_instnorm_apply(const float* x, const double* x_stats, const float* r, const double* r_stats, int N, int HW, int C,
-                        int relu_inner, int relu_outer, float* out_plain, float* out_cat3, void* stream) {
-  return instnorm_apply(x, x_stats, r, r_stats, N, HW, C, relu_inner, relu_outer, out_plain, out_cat3, ST(stream));
+                        int relu_inner, int relu_outer, float* out, void* stream) {
+  return instnorm_apply(x, x_stats, r, r_stats, N, HW, C, relu_inner, relu_outer, out, ST(stream));
 }
-int nmrf_split_cat3(const float* x, int64_t rows, int C, float* out, void* stream) {
-  return split_cat3(x, (long long)rows, C, out, ST(stream));
-}
-int nmrf_image_prep(const float* img1_nhwc, const float* img2_nhwc, int B, int H, int W, float* out_cat3, void* stream) {
-  return image_prep(img1_nhwc, img2_nhwc, B, H, W, out_cat3, ST(stream));
+int nmrf_image_prep(const float* img1, const float* img2, int B, int H, int W, int Hp, int Wp, int64_t stride_b, int64_t stride_c,
+                    int64_t stride_y, int64_t stride_x, float* out_cat3, void* stream) {
+  return image_prep(img1, img2, B, H, W, Hp, Wp, stride_b, stride_c, stride_y, stride_x, out_cat3, ST(stream));
 }
 int nmrf_avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_cat3, void* stream) {
   return avgpool2_split(x, N, h, w, C, out_a, out_b, out_cat3, ST(stream));
@@ -211,6 +215,13 @@ int nmrf_select_median(const float* delta, const float* score, const float* labe
 int nmrf_refine_tail(const float* delta, const float* disp_curr, const float* disp_curr_lo, int B, int h4, int w4, int Hp4,
                      int Wp4, int top, int left, int H, int W, float* disp_pred, float* disp, void* stream) {
   return refine_tail(delta, disp_curr, disp_curr_lo, B, h4, w4, Hp4, Wp4, top, left, H, W, disp_pred, disp, ST(stream));
+}
+int nmrf_disp_metrics(const float* disp_pr, const float* disp_gt, const uint8_t* valid_gt, int B, int64_t HW, float max_disp,
+                      const float* thresholds_host, int n_thres, double* acc, void* stream) {
+  return disp_metrics(disp_pr, disp_gt, valid_gt, B, (long long)HW, max_disp, thresholds_host, n_thres, acc, ST(stream));
+}
+int nmrf_disp_to_kitti_u16(const float* disp, int64_t n, uint16_t* out, void* stream) {
+  return disp_to_kitti_u16(disp, (long long)n, out, ST(stream));
 }
 int nmrf_ms_deform_attn_forward(const float* value, const int64_t* shapes, const int64_t* level_start, const float* loc,
                                 const float* attn, int N, int S, int M, int Dh, int L, int Lq, int P, float* out,

@@ -56,6 +56,11 @@ __device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], con
   mma8(c, ah, b0h, b1h);
 }
 
+// Long accumulations (P.V over 18 + 7 k-steps): mma.sync updates its accumulator with round-toward-zero like tcgen05 (relative
+// bias -1.6e-8 per mma into the same registers, tools/precision_probe.py), so the kernel keeps the small lo.hi / hi.lo
+// products of all k-steps in a separate accumulator (where truncation is relative to THEIR small magnitude) and adds it to
+// the hi.hi accumulator once.
+
 template <int WS, int K>
 struct Geo {
   static constexpr int P = WS * WS, Tw = P * K, NB = Tw / 16, NT = Tw / 8;
@@ -291,6 +296,13 @@ window_attention_mma_kernel(const WinMmaParams p) {
   for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
     for (int c = 0; c < 4; ++c) oc[nt][c] = 0.f;
+  // P . V  and  (bucket sums) . Rv_sub  over 18 + 7 k-steps: the small lo.hi / hi.lo products go to their OWN accumulator (os),
+  // the hi.hi products to oc, and the two are added once at the end (see mma_small)
+  float os[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) os[nt][c] = 0.f;
   {
     // A fragment = C fragment of P with the k index permuted: fragment column t <-> key 2t, column t+4 <-> key 2t+1
     const float* vb = Vs + (wl * Tw + 2 * t) * LD + g;
@@ -300,7 +312,13 @@ window_attention_mma_kernel(const WinMmaParams p) {
       split(sc[ks][0], ph[0], pl[0]); split(sc[ks][2], ph[1], pl[1]);
       split(sc[ks][1], ph[2], pl[2]); split(sc[ks][3], ph[3], pl[3]);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) mma3(oc[nt], ph, pl, vb[ks * 8 * LD + nt * 8], vb[ks * 8 * LD + LD + nt * 8]);
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t b0h, b0l, b1h, b1l;
+        split(vb[ks * 8 * LD + nt * 8], b0h, b0l); split(vb[ks * 8 * LD + LD + nt * 8], b1h, b1l);
+        mma8(os[nt], pl, b0h, b1h);
+        mma8(os[nt], ph, b0l, b1l);
+        mma8(oc[nt], ph, b0h, b1h);
+      }
     }
   }
   {
@@ -325,10 +343,19 @@ window_attention_mma_kernel(const WinMmaParams p) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) split(av[c], ah[c], al[c]);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-        mma3(oc[nt], ah, al, __ldg(rv + (size_t)rrow[0] * kQkv + nt * 8 + g), __ldg(rv + (size_t)rrow[1] * kQkv + nt * 8 + g));
+      for (int nt = 0; nt < 4; ++nt) {
+        uint32_t b0h, b0l, b1h, b1l;
+        split(__ldg(rv + (size_t)rrow[0] * kQkv + nt * 8 + g), b0h, b0l); split(__ldg(rv + (size_t)rrow[1] * kQkv + nt * 8 + g), b1h, b1l);
+        mma8(os[nt], al, b0h, b1h);
+        mma8(os[nt], ah, b0l, b1l);
+        mma8(oc[nt], ah, b0h, b1h);
+      }
     }
   }
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) oc[nt][c] += os[nt][c];
   if (live) {
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
     float* o0 = p.out + (size_t)tok_row[slot0 + g] * kEmbed + head * 32 + 2 * t;

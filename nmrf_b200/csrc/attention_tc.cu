@@ -219,13 +219,14 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     __syncthreads();
     if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // fresh accumulator: the small lo.hi / hi.lo products first, then hi.hi -- the tensor core's round-toward-zero accumulator
+      // update (gemm_tc6.cu) then only bites on the four (eight for PV) main products
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t adv = (uint64_t)(ks * 2);
-        umma_tf32(tmem, dQl + adv, dKh + adv, idesc_s, ks > 0 ? 1u : 0u);
-        umma_tf32(tmem, dQh + adv, dKl + adv, idesc_s, 1u);
-        umma_tf32(tmem, dQh + adv, dKh + adv, idesc_s, 1u);
-      }
+      for (int ks = 0; ks < 4; ++ks) umma_tf32(tmem, dQl + (uint64_t)(ks * 2), dKh + (uint64_t)(ks * 2), idesc_s, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) umma_tf32(tmem, dQh + (uint64_t)(ks * 2), dKl + (uint64_t)(ks * 2), idesc_s, 1u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) umma_tf32(tmem, dQh + (uint64_t)(ks * 2), dKh + (uint64_t)(ks * 2), idesc_s, 1u);
       umma_commit(&sm.bar_s);
     }
     __syncwarp();
@@ -279,14 +280,16 @@ stripe_attention_tc_kernel(const float* __restrict__ qkv, int B, int h, int w, i
     __syncthreads();
     if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // keys 8 ks .. +7: V_c^T tile ks / 4, 32-byte step ks % 4 inside its swizzle rows; P columns 8 ks .. +7.  Small products first.
 #pragma unroll
-      for (int ks = 0; ks < AT_KC / 8; ++ks) {
-        // keys 8 ks .. +7: V_c^T tile ks / 4, 32-byte step ks % 4 inside its swizzle rows; P columns 8 ks .. +7
-        const uint64_t adv = (uint64_t)((ks >> 2) * (4096 >> 4) + (ks & 3) * 2);
-        umma_tf32_ta(tmem + AT_COL_O, tmem + AT_COL_PL + ks * 8, dVh + adv, idesc_o, ks > 0 ? 1u : 0u);
-        umma_tf32_ta(tmem + AT_COL_O, tmem + AT_COL_PH + ks * 8, dVl + adv, idesc_o, 1u);
-        umma_tf32_ta(tmem + AT_COL_O, tmem + AT_COL_PH + ks * 8, dVh + adv, idesc_o, 1u);
-      }
+      for (int ks = 0; ks < AT_KC / 8; ++ks)
+        umma_tf32_ta(tmem + AT_COL_O, tmem + AT_COL_PL + ks * 8, dVh + (uint64_t)((ks >> 2) * (4096 >> 4) + (ks & 3) * 2), idesc_o, ks > 0 ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < AT_KC / 8; ++ks)
+        umma_tf32_ta(tmem + AT_COL_O, tmem + AT_COL_PH + ks * 8, dVl + (uint64_t)((ks >> 2) * (4096 >> 4) + (ks & 3) * 2), idesc_o, 1u);
+#pragma unroll
+      for (int ks = 0; ks < AT_KC / 8; ++ks)
+        umma_tf32_ta(tmem + AT_COL_O, tmem + AT_COL_PH + ks * 8, dVh + (uint64_t)((ks >> 2) * (4096 >> 4) + (ks & 3) * 2), idesc_o, 1u);
       umma_commit(&sm.bar_o);
     }
     __syncwarp();

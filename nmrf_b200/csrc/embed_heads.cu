@@ -234,3 +234,90 @@ int refine_tail(const float* delta, const float* disp_curr, const float* disp_cu
 }
 
 }  // namespace nmrf
+
+// ---- N4: the step after the path in every pipeline of the reference -----------------------------------------------------
+//   disparity metrics (DispEvaluator.process, nmrf/utils/evaluation.py:345-359) reduced on the device, and the KITTI 16-bit
+//   disparity encoding (writeDispKITTI, nmrf/utils/frame_utils.py:237-239)
+namespace nmrf {
+namespace {
+
+constexpr int kMaxThres = 8;
+struct MetricThres { float t[kMaxThres]; int n; };
+
+// per image: acc[0] = #valid, acc[1] = sum |pr - gt|, acc[2] = #D1 outliers ((e > 3) & (e / gt > 0.05)), acc[3 + i] = #(e > t_i);
+// all over the valid pixels (valid_gt & gt < max_disp, or gt < max_disp when only_valid is off).  One block-level reduction
+// per 4096 pixels, one double atomicAdd per block and statistic: the sums are exact counts / double sums.
+__global__ void __launch_bounds__(256)
+disp_metrics_kernel(const float* __restrict__ pr, const float* __restrict__ gt, const uint8_t* __restrict__ valid_gt,
+                    long long HW, float max_disp, MetricThres th, double* __restrict__ acc) {
+  const int b = blockIdx.y, nstat = 3 + th.n;
+  const float* p = pr + (size_t)b * HW;
+  const float* g = gt + (size_t)b * HW;
+  const uint8_t* v = valid_gt ? valid_gt + (size_t)b * HW : nullptr;
+  double s[3 + kMaxThres];
+#pragma unroll
+  for (int i = 0; i < 3 + kMaxThres; ++i) s[i] = 0.0;
+  const long long base = (long long)blockIdx.x * 4096;
+  for (int it = 0; it < 16; ++it) {
+    const long long i = base + it * 256 + threadIdx.x;
+    if (i >= HW) break;
+    const float gi = g[i];
+    const bool ok = (gi < max_disp) && (!v || v[i] != 0);
+    if (!ok) continue;
+    const float e = fabsf(p[i] - gi);
+    s[0] += 1.0;
+    s[1] += (double)e;
+    s[2] += (e > 3.f && __fdiv_rn(e, gi) > 0.05f) ? 1.0 : 0.0;
+#pragma unroll
+    for (int k = 0; k < kMaxThres; ++k)
+      if (k < th.n) s[3 + k] += (e > th.t[k]) ? 1.0 : 0.0;
+  }
+  __shared__ double red[8][3 + kMaxThres];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int k = 0; k < nstat; ++k) {
+    double x = s[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    if (lane == 0) red[warp][k] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < nstat) {
+    double x = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) x += red[w][threadIdx.x];
+    if (x != 0.0) atomicAdd(acc + (size_t)b * nstat + threadIdx.x, x);
+  }
+}
+
+// out = (uint16) round_half_even(disp * 256): numpy's `np.round(disp * 256).astype(np.uint16)` for in-range values; like
+// numpy on x86 the conversion goes through int32, i.e. values beyond 65535 wrap modulo 2^16 (KITTI disparities are < 256 px)
+__global__ void disp_to_kitti_u16_kernel(const float* __restrict__ disp, long long n, uint16_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = (uint16_t)(int)rintf(disp[i] * 256.f);
+}
+
+}  // namespace
+
+int disp_metrics(const float* pr, const float* gt, const uint8_t* valid_gt, int B, long long HW, float max_disp,
+                 const float* thresholds_host, int n_thres, double* acc, cudaStream_t stream) {
+  NMRF_REQUIRE(pr && gt && acc && B > 0 && HW > 0, "disp_metrics: bad arguments");
+  NMRF_REQUIRE(n_thres >= 0 && n_thres <= kMaxThres && (n_thres == 0 || thresholds_host), "disp_metrics: %d thresholds (max %d)", n_thres, kMaxThres);
+  MetricThres th;
+  th.n = n_thres;
+  for (int i = 0; i < kMaxThres; ++i) th.t[i] = i < n_thres ? thresholds_host[i] : 0.f;
+  dim3 grid((unsigned)((HW + 4095) / 4096), B);
+  disp_metrics_kernel<<<grid, 256, 0, stream>>>(pr, gt, valid_gt, HW, max_disp, th, acc);
+  count_launch();
+  return check_launch("disp_metrics");
+}
+
+int disp_to_kitti_u16(const float* disp, long long n, uint16_t* out, cudaStream_t stream) {
+  NMRF_REQUIRE(disp && out && n >= 0, "disp_to_kitti_u16: bad arguments");
+  if (n == 0) return NMRF_OK;
+  disp_to_kitti_u16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(disp, n, out);
+  count_launch();
+  return check_launch("disp_to_kitti_u16");
+}
+
+}  // namespace nmrf

@@ -1,11 +1,11 @@
 // N2 ("next"): element-wise glue of the convolutional feature extractor and the conv heads, NHWC.
-// The convolutions themselves stay library calls (cuDNN implicit GEMM on [x_hi | x_lo | x_hi] x [w_hi | w_hi | w_lo],
-// i.e. error-compensated 3xTF32 in ONE call); what is fused here is everything between two convolutions, which in torch
-// took 5 of the encoder's 7.8 ms (NCHW<->NHWC copies around InstanceNorm, batch_norm statistics / transform, ReLU,
-// residual add, the hi/lo split and the `y +=` accumulations of three separate convolutions):
+// The convolutions are nmrf_conv2d (gemm_tc6.cu, CONV mode); fused here is everything between two convolutions, which in
+// torch took 5 of the encoder's 7.8 ms (NCHW<->NHWC copies around InstanceNorm, batch_norm statistics / transform, ReLU,
+// residual add):
 //   instnorm_stats : per (sample, channel) sum and sum of squares over H*W   (reference: nn.InstanceNorm2d, backbone.py:28-41)
-//   instnorm_apply : y = relu?(IN(x)) [+ r | + IN(r)] -> relu? -> plain fp32 and/or the [hi | lo | hi] operand of the next conv
-//   split_cat3     : plain tensor -> [hi | lo | hi]
+//   instnorm_apply : y = relu?(IN(x)) [+ r | + IN(r)] -> relu?
+//   image_prep     : N3 prologue (replicate pad, normalisation, left/right batching, the stem's zero border)
+//   avgpool2_split : feat@1/8 = avg_pool2d(feat@1/4) (backbone.py:96-98)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -56,7 +56,7 @@ __device__ __forceinline__ void mean_rstd(const double* st, int HW, float& mean,
 
 struct ApplyArgs {
   const float* x; const double* xs; const float* r; const double* rs;
-  float* plain; float* cat3;
+  float* plain;
   int HW, C, relu_inner, relu_outer;
   long long per_sample4;                            // HW*C/4
 };
@@ -110,50 +110,35 @@ __global__ void instnorm_apply_kernel(const ApplyArgs a) {
       for (int j = 0; j < 4; ++j) o[j] = fmaxf(o[j], 0.f);
     }
     if (a.plain) *reinterpret_cast<float4*>(a.plain + pix * a.C + c) = make_float4(o[0], o[1], o[2], o[3]);
-    if (a.cat3) {
-      float h[4], l[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { h[j] = rna_tf32_fast(o[j]); l[j] = rna_tf32_fast(o[j] - h[j]); }
-      float* d = a.cat3 + pix * 3 * a.C + c;
-      const float4 h4 = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(d) = h4;
-      *reinterpret_cast<float4*>(d + a.C) = make_float4(l[0], l[1], l[2], l[3]);
-      *reinterpret_cast<float4*>(d + 2 * a.C) = h4;
-    }
   }
 }
 
-// generic (any C): one thread per element
-__global__ void split_cat3_kernel(const float* __restrict__ x, long long rows, int C, float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * C) return;
-  const long long r = i / C;
-  const int c = (int)(i % C);
-  const float v = x[i], h = rna_tf32_fast(v), l = rna_tf32_fast(v - h);
-  float* d = out + r * 3 * C + c;
-  d[0] = h; d[C] = l; d[2 * C] = h;
-}
-
-// images [B,H,W,3] (channels_last storage of the reference's [B,3,H,W] tensors), left then right -> [2B,H,W,9] =
-// [hi | lo | hi] of 2 (x / 255) - 1 (backbone.py:86), the operand of the stem convolution
-__global__ void image_prep_kernel(const float* __restrict__ img1, const float* __restrict__ img2, long long per_img, long long total,
+// left / right images -> [2B, Hp+6, Wp+8, 4]: 2 (x / 255) - 1 (backbone.py:86) as RGB0 pixels inside the stem's zero border;
+// thread = one pixel of the output [2B, Hp+6, Wp+8] (both images, zero border included); the replicate padding of InputPadder
+// (frame_utils.py:273-275, right / bottom) is a clamp of the source coordinate, and the source may be NCHW or NHWC (strides)
+__global__ void image_prep_kernel(const float* __restrict__ img1, const float* __restrict__ img2, int H, int W, int Hp, int Wp,
+                                  long long sb, long long sc, long long sy, long long sx, long long per_img, long long total,
                                   float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // pixel index over both images
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
-  const float* src = (i < per_img ? img1 + i * 3 : img2 + (i - per_img) * 3);
-  float* d = out + i * 9;
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const float v = 2.f * __fdiv_rn(src[c], 255.f) - 1.f;
-    const float h = rna_tf32_fast(v), l = rna_tf32_fast(v - h);
-    d[c] = h; d[3 + c] = l; d[6 + c] = h;
+  const int Wb = Wp + 8, Hb = Hp + 6;
+  const long long j = i < per_img ? i : i - per_img;
+  const int x = (int)(j % Wb) - 3, y = (int)((j / Wb) % Hb) - 3;
+  const long long b = j / ((long long)Wb * Hb);
+  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x >= 0 && x < Wp && y >= 0 && y < Hp) {
+    const float* src = (i < per_img ? img1 : img2) + b * sb + (long long)min(y, H - 1) * sy + (long long)min(x, W - 1) * sx;
+    o.x = 2.f * __fdiv_rn(src[0], 255.f) - 1.f;
+    o.y = 2.f * __fdiv_rn(src[sc], 255.f) - 1.f;
+    o.z = 2.f * __fdiv_rn(src[2 * sc], 255.f) - 1.f;
   }
+  reinterpret_cast<float4*>(out)[i] = o;
 }
 
 // 2x2 average pool of an NHWC map (backbone.py:96-98) -> plain halves (first N/2 samples to out_a, the rest to out_b: the hot
 // path's f1_8 / f2_8) and the [hi | lo | hi] operand of the heads' 3x3 convolution; thread = 4 channels of one output pixel
 __global__ void avgpool2_split_kernel(const float* __restrict__ x, int N, int h, int w, int C, float* __restrict__ out_a,
-                                      float* __restrict__ out_b, float* __restrict__ cat3) {
+                                      float* __restrict__ out_b, float* __restrict__ out_all) {
   const int c4n = C >> 2, ho = h >> 1, wo = w >> 1;
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)N * ho * wo * c4n;
@@ -172,30 +157,24 @@ __global__ void avgpool2_split_kernel(const float* __restrict__ x, int N, int h,
   const int half = N >> 1;
   float* plain = n < half ? out_a + pix * C + c : out_b + (pix - (size_t)half * ho * wo) * C + c;
   *reinterpret_cast<float4*>(plain) = make_float4(o[0], o[1], o[2], o[3]);
-  float hh[4], ll[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) { hh[j] = rna_tf32_fast(o[j]); ll[j] = rna_tf32_fast(o[j] - hh[j]); }
-  float* d = cat3 + pix * 3 * C + c;
-  const float4 h4 = make_float4(hh[0], hh[1], hh[2], hh[3]);
-  *reinterpret_cast<float4*>(d) = h4;
-  *reinterpret_cast<float4*>(d + C) = make_float4(ll[0], ll[1], ll[2], ll[3]);
-  *reinterpret_cast<float4*>(d + 2 * C) = h4;
+  if (out_all) *reinterpret_cast<float4*>(out_all + pix * C + c) = make_float4(o[0], o[1], o[2], o[3]);
 }
 }  // namespace
 
-int image_prep(const float* img1, const float* img2, int B, int H, int W, float* out, cudaStream_t stream) {
-  NMRF_REQUIRE(img1 && img2 && out && B > 0 && H > 0 && W > 0, "image_prep: bad arguments");
-  const long long per = (long long)B * H * W, total = 2 * per;
-  image_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img1, img2, per, total, out);
+int image_prep(const float* img1, const float* img2, int B, int H, int W, int Hp, int Wp, long long sb, long long sc,
+               long long sy, long long sx, float* out, cudaStream_t stream) {
+  NMRF_REQUIRE(img1 && img2 && out && B > 0 && H > 0 && W > 0 && Hp >= H && Wp >= W, "image_prep: bad arguments");
+  const long long per = (long long)B * (Hp + 6) * (Wp + 8), total = 2 * per;
+  image_prep_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(img1, img2, H, W, Hp, Wp, sb, sc, sy, sx, per, total, out);
   count_launch();
   return check_launch("image_prep");
 }
 
-int avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* cat3, cudaStream_t stream) {
-  NMRF_REQUIRE(x && out_a && out_b && cat3, "avgpool2_split: null pointer");
+int avgpool2_split(const float* x, int N, int h, int w, int C, float* out_a, float* out_b, float* out_all, cudaStream_t stream) {
+  NMRF_REQUIRE(x && out_a && out_b, "avgpool2_split: null pointer");
   NMRF_REQUIRE(N > 0 && N % 2 == 0 && h >= 2 && w >= 2 && C % 4 == 0, "avgpool2_split: N=%d h=%d w=%d C=%d", N, h, w, C);
   const long long total = (long long)N * (h / 2) * (w / 2) * (C / 4);
-  avgpool2_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, N, h, w, C, out_a, out_b, cat3);
+  avgpool2_split_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, N, h, w, C, out_a, out_b, out_all);
   count_launch();
   return check_launch("avgpool2_split");
 }
@@ -216,12 +195,12 @@ int instnorm_stats(const float* x, int N, int HW, int C, double* stats, cudaStre
 }
 
 int instnorm_apply(const float* x, const double* x_stats, const float* r, const double* r_stats, int N, int HW, int C,
-                   int relu_inner, int relu_outer, float* out_plain, float* out_cat3, cudaStream_t stream) {
-  NMRF_REQUIRE(x && N > 0 && HW > 0 && (out_plain || out_cat3), "instnorm_apply: bad arguments");
+                   int relu_inner, int relu_outer, float* out_plain, cudaStream_t stream) {
+  NMRF_REQUIRE(x && N > 0 && HW > 0 && out_plain, "instnorm_apply: bad arguments");
   NMRF_REQUIRE(C % 4 == 0, "instnorm_apply: C=%d must be a multiple of 4", C);
   NMRF_REQUIRE(r || !r_stats, "instnorm_apply: r_stats without r");
   ApplyArgs a;
-  a.x = x; a.xs = x_stats; a.r = r; a.rs = r_stats; a.plain = out_plain; a.cat3 = out_cat3;
+  a.x = x; a.xs = x_stats; a.r = r; a.rs = r_stats; a.plain = out_plain;
   a.HW = HW; a.C = C; a.relu_inner = relu_inner; a.relu_outer = relu_outer;
   NMRF_REQUIRE(C <= 2048, "instnorm_apply: C=%d too large", C);
   a.per_sample4 = (long long)HW * (C / 4);
@@ -229,14 +208,6 @@ int instnorm_apply(const float* x, const double* x_stats, const float* r, const 
   instnorm_apply_kernel<<<dim3(chunks, N), 256, 4 * C * sizeof(float), stream>>>(a);
   count_launch();
   return check_launch("instnorm_apply");
-}
-
-int split_cat3(const float* x, long long rows, int C, float* out, cudaStream_t stream) {
-  NMRF_REQUIRE(x && out && rows > 0 && C > 0, "split_cat3: bad arguments");
-  const long long n = rows * C;
-  split_cat3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(x, rows, C, out);
-  count_launch();
-  return check_launch("split_cat3");
 }
 
 }  // namespace nmrf

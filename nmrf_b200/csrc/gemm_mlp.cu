@@ -1,7 +1,14 @@
 // Fused message-passing tail on tcgen05: one kernel per block for everything that is row-local after the attention
-//     x1 = att . Wproj^T + b_proj + x                  (NMP.py:358-359,570-571: proj + residual; the residual x is PRELOADED
-//                                                       into the accumulator in full fp32 -- tcgen05.st -- before the MMAs)
-//     x  = x1 + fc2( GELU( fc1( LN2(x1) ) ) )           (NMP.py:362-363,572-573; timm Mlp)
+//     x1 = x + (att . Wproj^T + b_proj)                (NMP.py:358-359,570-571: proj + residual)
+//     x  = x1 + (fc2( GELU( fc1( LN2(x1) ) ) ) + b_fc2) (NMP.py:362-363,572-573; timm Mlp)
+// The residual stream lives in fp32 REGISTERS of the worker threads (thread = row, 32 columns each), never in a tensor-memory
+// accumulator: the tensor core's accumulator update rounds toward zero (measured, tools/precision_probe.py: a relative bias of
+// -1.6e-8 per MMA accumulated into the same columns, i.e. -7.7e-7 for K = 128 and -3e-6 for K = 512, against +-1e-10 for fp32
+// FMAs), and every such truncation is relative to the magnitude IN the accumulator.  With x preloaded there (round 1) the 240
+// MMAs of a tile shaved 7e-6 |x| off the residual stream per block -- 35 times the error of the fp32 reference arithmetic and
+// the main source of flipped argmax / median decisions downstream.  Now the accumulators only ever hold the (small) updates,
+// fc2's accumulator is drained into the registers every four hidden chunks, and inside a fresh accumulator the small
+// lo.hi / hi.lo products are issued before the hi.hi ones; all sums that involve x are fp32 round-to-nearest adds.
 // instead of three token GEMMs.  The ablation of the stand-alone GEMMs (tools/gemm_bench.py) showed ~14 us of fill/drain
 // latency per launch and the [T,512] hidden activation (4x the token state, written by fc1 and re-read by fc2) as the
 // dominant costs; here a CTA takes a 128-row tile through the whole chain and the only HBM/L2 traffic per tile is
@@ -27,8 +34,7 @@
 //                                 only 2-3 MMAs (tools/probes/seq_probe.cu: 12 MMAs block the issuing thread for 600 of their 768
 //                                 cycles), so whatever one issuer spends between units (two barrier polls, elect, descriptors:
 //                                 ~500 cycles) is tensor idle time unless the other issuer's unit is executing meanwhile.
-// Arithmetic: 3xTF32 with RN hi / RN lo split as in gemm_tc6; LayerNorm two-pass in fp32 from the fp32
-// accumulator; GELU as gemm_tc6.
+// Arithmetic: 3xTF32 with RN hi / RN lo split as in gemm_tc6; LayerNorm two-pass in fp32 on x1; GELU as gemm_tc6.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -63,12 +69,14 @@ struct MSmem {
   uint64_t h_full[2];         // hidden chunk hi/lo in shared memory (16 warp arrivals)
   uint64_t h_free[2];         // fc2 MMAs of the chunk complete (commit)
   uint64_t acc0_final;        // all MMAs of the tile complete (commit)
-  uint64_t acc0_empty;        // final epilogue has read acc0 (8 warp arrivals)
+  uint64_t acc0_empty;        // final epilogue has read acc0 (16 warp arrivals)
+  uint64_t part_full;         // fc2 units 4d .. 4d+3 complete: acc0 holds their partial sum (commit; d = 0, 1, 2)
+  uint64_t part_drained;      // ... and every worker has added it to its registers (16 warp arrivals): acc0 may be overwritten
   uint32_t tmem_base;
   alignas(16) float gamma[128];
   alignas(16) float beta[128];
   alignas(16) float bmid[128];
-  alignas(16) float bout[128];
+  alignas(16) float bout[128];      // fc2 bias
   alignas(16) float b1[M_HID];
   float red[2][4][M_BM];      // LayerNorm partial sums: [pass][worker of the quarter][row]
 };
@@ -87,16 +95,21 @@ __device__ __forceinline__ uint32_t idesc_n(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
-// LN2 of x1 = acc0 + b_proj on the 16 worker warps: thread = row (TMEM lane), worker j of the lane quarter owns columns
-// 32 j .. 32 j + 31.  Two-pass like torch (mean, then squared deviations); the four workers of a quarter exchange their
-// partial sums through shared memory (named barrier 8 + quarter, 128 threads).  Result: hi / lo of the normalised row as the
-// A operand of fc1 in TMEM.
-__device__ __forceinline__ void ln_worker(MSmem& sm, uint32_t tmem_lane, int q, int row, int j, int lane) {
-  float v[32];
-  tmem_ld32(tmem_lane + (uint32_t)(j * 32), v);
+// x1 = x + (acc0 + b_proj) and LN2(x1) on the 16 worker warps: thread = row (TMEM lane), worker j of the lane quarter owns
+// columns 32 j .. 32 j + 31; on entry v holds the thread's slice of the residual x (zeros if there is none), on exit x1 -- it
+// stays in registers until the tile is stored.  Two-pass like torch (mean, then squared deviations); the four workers of a
+// quarter exchange their partial sums through shared memory (named barrier 8 + quarter, 128 threads).  Result: hi / lo of
+// the normalised row as the A operand of fc1 in TMEM.
+__device__ __forceinline__ void ln_worker(MSmem& sm, uint32_t tmem_lane, int q, int row, int j, int lane, float (&v)[32]) {
+  {
+    float u[32];
+    tmem_ld32(tmem_lane + (uint32_t)(j * 32), u);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += u[i] + sm.bmid[j * 32 + i];
+  }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { v[i] += sm.bmid[j * 32 + i]; s += v[i]; }
+  for (int i = 0; i < 32; ++i) s += v[i];
   sm.red[0][j][row] = s;
   asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(128) : "memory");
   const float mean = ((sm.red[0][0][row] + sm.red[0][1][row]) + (sm.red[0][2][row] + sm.red[0][3][row])) * (1.f / 128.f);
@@ -107,19 +120,20 @@ __device__ __forceinline__ void ln_worker(MSmem& sm, uint32_t tmem_lane, int q, 
   asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(128) : "memory");
   const float var = ((sm.red[1][0][row] + sm.red[1][1][row]) + (sm.red[1][2][row] + sm.red[1][3][row])) * (1.f / 128.f);
   const float rstd = 1.f / sqrtf(var + 1e-5f);
-  uint32_t hi[32], lo[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int k = j * 32 + i;
-    const float y = (v[i] - mean) * rstd * sm.gamma[k] + sm.beta[k];
-    const float h = rna_tf32_fast(y);
-    hi[i] = __float_as_uint(h);
-    lo[i] = __float_as_uint(lo_tf32(y, h));
+  for (int half16 = 0; half16 < 2; ++half16) {       // 16 columns at a time: x1 stays live, so keep the temporaries small
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int k = j * 32 + half16 * 16 + i;
+      const float y = (v[half16 * 16 + i] - mean) * rstd * sm.gamma[k] + sm.beta[k];
+      const float h = rna_tf32_fast(y);
+      hi[i] = __float_as_uint(h);
+      lo[i] = __float_as_uint(lo_tf32(y, h));
+    }
+    tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32 + half16 * 16), hi);
+    tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_LO + j * 32 + half16 * 16), lo);
   }
-  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32), hi);
-  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_HI + j * 32 + 16), hi + 16);
-  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_LO + j * 32), lo);
-  tmem_st16(tmem_lane + (uint32_t)(M_COL_ALN_LO + j * 32 + 16), lo + 16);
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncwarp();
@@ -164,6 +178,72 @@ __device__ __forceinline__ void gelu_worker(MSmem& sm, uint32_t tmem_lane, uint8
   mtrace(tp, 2048 + gc * 8 + 4);
 }
 
+// this thread's 32-column slice of the residual row (zeros without a residual / past the last row).  Plain (L1-cached) loads:
+// thread = row, so one instruction touches 32 different lines and the next one the neighbouring 16 bytes of the same lines
+__device__ __forceinline__ void load_residual(const nmrf_mlp_args& a, int grow, int j, float (&v)[32]) {
+  if (a.e_identity && grow < a.rows) {
+    const float4* p = reinterpret_cast<const float4*>(a.E + (size_t)grow * a.lde + j * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) { const float4 t = p[c]; v[c * 4] = t.x; v[c * 4 + 1] = t.y; v[c * 4 + 2] = t.z; v[c * 4 + 3] = t.w; }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = 0.f;
+  }
+}
+// v += this thread's 32 columns of acc0 (fp32 round-to-nearest adds, outside the tensor core)
+__device__ __forceinline__ void add_acc0(uint32_t tmem_lane, int j, float (&v)[32]) {
+  float u[32];
+  tmem_ld32(tmem_lane + (uint32_t)(j * 32), u);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] += u[i];
+}
+
+// Everything a worker thread does for one tile after phase 1: x1 and LayerNorm, the 16 hidden chunks, the three drains of
+// fc2's accumulator, the final sum and the store.  v: residual slice on entry.
+__device__ __forceinline__ void worker_tile(MSmem& sm, const nmrf_mlp_args& a, uint32_t tmem_lane, uint8_t* sH, int q, int row, int j,
+                                            int lane, int it, int grow, int rot, float (&v)[32], long long* tp) {
+  mbar_wait_warp(&sm.p1_full, it & 1);
+  mtrace(tp, 3968 + it * 8 + 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  ln_worker(sm, tmem_lane, q, row, j, lane, v);
+  mtrace(tp, 3968 + it * 8 + 1);
+#pragma unroll 1
+  for (int c = 0; c < M_NCH; ++c) {
+    gelu_worker(sm, tmem_lane, sH, row, j, (uint32_t)(it * M_NCH + c), sm.b1 + ((c + rot) & (M_NCH - 1)) * M_CH + j * 8, lane, tp);
+    if (c >= 4 && (c & 3) == 0) {
+      // fc2 units c-4 .. c-1 are complete (they were issued while this chunk went through GELU): move their partial sum out of
+      // the tensor-core accumulator; the issuer restarts acc0 with unit c once all 16 warps have done so
+      const uint32_t d = (uint32_t)it * 3 + (uint32_t)(c >> 2) - 1;
+      mbar_wait_warp(&sm.part_full, d & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      add_acc0(tmem_lane, j, v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive_m(&sm.part_drained);
+    }
+  }
+  // ---- final: y = x1 + (fc2 partial of units 12..15 + b_fc2), straight from the registers (thread = row: 128 contiguous bytes)
+  mbar_wait_warp(&sm.acc0_final, it & 1);
+  mtrace(tp, 3968 + it * 8 + 2);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  {
+    float u[32];
+    tmem_ld32(tmem_lane + (uint32_t)(j * 32), u);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive_m(&sm.acc0_empty);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] += u[i] + sm.bout[j * 32 + i];
+  }
+  if (grow < a.rows) {
+    float4* dst = reinterpret_cast<float4*>(a.Y + (size_t)grow * a.ldy + j * 32);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+  }
+  mtrace(tp, 3968 + it * 8 + 3);
+}
+
+// 608 threads = 19 warps = up to 5 warps per register-file partition (16 384 registers): at most 96 registers per thread
 __global__ void __launch_bounds__(M_BLOCK, 1)
 mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
   extern __shared__ __align__(1024) uint8_t dsm[];
@@ -179,11 +259,9 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
 #else
   long long* const tp = nullptr;
 #endif
-  // phase 1 per tile: n_e k-blocks of E preloaded into acc0 (e_identity: E is the residual, added exactly), then n1 weight
-  // units against the k-blocks of X (and of E when it is an ordinary concatenated operand)
-  const int n_e = a.e_identity ? a.Ke / M_BK : 0;
-  const int n1 = (a.e_identity ? a.Kx : a.Kx + a.Ke) / M_BK;      // phase-1 weight units per tile
-  const int nb = n_e + n1;                         // phase-1 k-blocks the producers handle per tile
+  // phase 1 per tile: n1 weight units against the k-blocks of X (and of E when it is an ordinary concatenated operand; a
+  // RESIDUAL E -- e_identity -- never enters the tensor core: the workers add it in registers)
+  const int n1 = (a.e_identity ? a.Kx : a.Kx + a.Ke) / M_BK;
   const int upt = n1 + 2 * M_NCH;                  // weight units per tile
   const int tstep = gridDim.x;
   // every CTA starts at its own rotation of the k-block order (phase 1) and of the hidden-chunk order (phase 3), so that the
@@ -200,7 +278,8 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
     mbar_init(&sm.p1_full, 1); mbar_init(&sm.aln_full, M_WORKERS);
     for (int i = 0; i < 4; ++i) { mbar_init(&sm.acc1_full[i], 1); mbar_init(&sm.acc1_empty[i], M_WORKERS); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sm.h_full[i], M_WORKERS); mbar_init(&sm.h_free[i], 1); }
-    mbar_init(&sm.acc0_final, 1); mbar_init(&sm.acc0_empty, M_EPI_WARPS);
+    mbar_init(&sm.acc0_final, 1); mbar_init(&sm.acc0_empty, M_WORKERS);
+    mbar_init(&sm.part_full, 1); mbar_init(&sm.part_drained, M_WORKERS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < 128) { sm.gamma[tid] = a.ln_gamma[tid]; sm.beta[tid] = a.ln_beta[tid]; sm.bmid[tid] = a.bias_mid[tid]; sm.bout[tid] = a.bias_out[tid]; }
@@ -211,7 +290,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
   const uint32_t tmem = sm.tmem_base;
 
   if (warp < 8) {
-    // =============================================== producers (phase 1) + GELU workers 0, 1 ===============================================
+    // =============================================== producers (phase 1) + workers 0, 1 ===============================================
     const int a_row = (warp & 3) * 32 + lane, a_c0 = (warp >> 2) * 4;
     const uint32_t a_lane = ((uint32_t)((warp & 3) * 32)) << 16;
     const int f_c = tid & 7, f_r = tid >> 3;
@@ -229,14 +308,14 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
         f_ok |= (ok ? 1u : 0u) << j;
         const int gr = ok ? grow : 0;
         f_x[j] = a.X + (size_t)gr * a.ldx + f_c * 4;
-        f_e[j] = a.E ? a.E + (size_t)gr * a.lde + f_c * 4 - a.Kx : a.X;
+        f_e[j] = (a.E && !a.e_identity) ? a.E + (size_t)gr * a.lde + f_c * 4 - a.Kx : a.X;
       }
     };
     if (f_t < ntiles) fetch_tile();
     auto fetch_next = [&](uint32_t stage) {
       if (f_t < ntiles) {
         const uint32_t dst = smem_u32(sRaw(stage));
-        const int k0 = f_kb < n_e ? a.Kx + f_kb * M_BK : ((f_kb - n_e + rot) % n1) * M_BK;
+        const int k0 = ((f_kb + rot) % n1) * M_BK;
         const bool in_x = k0 + f_c * 4 < a.Kx;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -244,71 +323,57 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
           const float* src = (in_x ? f_x[j] : f_e[j]) + k0;
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(f_r + 32 * j, f_c)), "l"(ok ? src : a.X), "r"(ok ? 16 : 0));
         }
-        if (++f_kb == nb) { f_kb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
+        if (++f_kb == n1) { f_kb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     fetch_next(0); fetch_next(1);
-    uint32_t pu = 0;          // phase-1 units produced so far by this CTA: ring stage pu % 3, A buffer pu & 1, hand-off barrier 1 + pu % 3
+    uint32_t pu = 0;          // phase-1 units produced so far by this CTA: ring stage pu % 3, A buffer j % 4, hand-off barrier 1 + pu % 3
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
-      for (int kb = 0; kb < nb; ++kb, ++pu) {
+      for (int j = 0; j < n1; ++j, ++pu) {
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(M_RAW_BAR), "r"(M_PROD) : "memory");
         // the stage consumed one unit ago is free again (every producer is past its reads): re-arm it two k-blocks ahead
         fetch_next((pu + 2) % M_RAW);
         const uint8_t* raw = sRaw(pu % M_RAW);
-        float vv[16];
+        uint32_t hi[16], lo[16];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const float4 v = *reinterpret_cast<const float4*>(raw + swz(a_row, a_c0 + cc));
-          vv[cc * 4] = v.x; vv[cc * 4 + 1] = v.y; vv[cc * 4 + 2] = v.z; vv[cc * 4 + 3] = v.w;
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float h = rna_tf32_fast(vv[e]);
+            hi[cc * 4 + e] = __float_as_uint(h);
+            lo[cc * 4 + e] = __float_as_uint(lo_tf32(vv[e], h));
+          }
         }
         // TMEM columns written below were last touched by the previous tile: its MMAs (A buffers alias the fc1 accumulators
-        // and LN2(x1)) and its final epilogue (acc0) must be done
-        if (it > 0 && kb == 0) {
+        // and LN2(x1)) and its final read of acc0 must be done
+        if (it > 0 && j == 0) {
           mbar_wait_warp(&sm.acc0_final, (it - 1) & 1);
           mbar_wait_warp(&sm.acc0_empty, (it - 1) & 1);
         }
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (kb < n_e) {
-          // residual: 16 fp32 values of this row straight into the accumulator columns 32 kb + 4 a_c0 .. + 15
-          uint32_t r[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(vv[i]);
-          tmem_st16(tmem + a_lane + (uint32_t)(kb * M_BK + a_c0 * 4), r);
-        } else {
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float h = rna_tf32_fast(vv[i]);
-            hi[i] = __float_as_uint(h);
-            lo[i] = __float_as_uint(lo_tf32(vv[i], h));
-          }
-          // A buffer j % 4 (TMEM columns of the fc1 accumulators and of LN2(x1), both idle in phase 1): free once the MMAs of
-          // the weight unit four back are complete.  The producers wait for the unit THREE back: the `done` barriers rotate
-          // with the three weight slots, and a wait further back could miss its phase (the barrier would be two ahead).
-          const int j = kb - n_e;
-          if (j >= M_NB) {
-            const uint32_t g = (uint32_t)it * upt + j - M_NB;
-            mbar_wait_warp(&sm.done[g % M_NB], (g / M_NB) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          }
-          const uint32_t ta = tmem + a_lane + abuf_col(j % M_ABUF) + (uint32_t)(a_c0 * 4);
-          tmem_st16(ta, hi);
-          tmem_st16(ta + 32, lo);
+        // A buffer j % 4 (TMEM columns of the fc1 accumulators and of LN2(x1), both idle in phase 1): free once the MMAs of
+        // the weight unit four back are complete.  The producers wait for the unit THREE back: the `done` barriers rotate
+        // with the three weight slots, and a wait further back could miss its phase (the barrier would be two ahead).
+        if (j >= M_NB) {
+          const uint32_t g = (uint32_t)it * upt + j - M_NB;
+          mbar_wait_warp(&sm.done[g % M_NB], (g / M_NB) & 1);
         }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t ta = tmem + a_lane + abuf_col(j % M_ABUF) + (uint32_t)(a_c0 * 4);
+        tmem_st16(ta, hi);
+        tmem_st16(ta + 32, lo);
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.arrive %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
       }
       // LayerNorm and phase 3: the producers are workers 0 and 1 of their lane quarter
-      mbar_wait_warp(&sm.p1_full, it & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      ln_worker(sm, tmem + a_lane, warp & 3, a_row, warp >> 2, lane);
-      for (int c = 0; c < M_NCH; ++c)
-        gelu_worker(sm, tmem + a_lane, sH, a_row, warp >> 2, (uint32_t)(it * M_NCH + c),
-                    sm.b1 + ((c + rot) & (M_NCH - 1)) * M_CH + (warp >> 2) * 8, lane, nullptr);
+      float v[32];
+      load_residual(a, t * M_BM + a_row, warp >> 2, v);
+      worker_tile(sm, a, tmem + a_lane, sH, warp & 3, a_row, warp >> 2, lane, it, t * M_BM + a_row, rot, v, nullptr);
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == M_MMA_WARP || warp == M_MMA2_WARP) {
@@ -319,7 +384,8 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
     uint32_t pu = 0;          // phase-1 unit counter (A buffers / hand-off barriers)
     uint32_t gc = 0;          // global hidden-chunk counter of the tile's first chunk
     auto wait_b = [&](uint32_t unit) { mbar_wait_warp(&sm.full_b[unit % M_NB], (unit / M_NB) & 1); };
-    // F1 unit: fc1 rows of one hidden chunk (N = 32) over the whole K = 128; A = LN2(x1) from TMEM
+    // F1 unit: fc1 rows of one hidden chunk (N = 32) over the whole K = 128 into a FRESH accumulator; A = LN2(x1) from TMEM.
+    // The small products first: while the accumulator is small its round-toward-zero update loses nothing that matters.
     auto issue_f1 = [&](uint32_t cg) {
       if (cg >= 4) {                                                       // accumulator cg & 3 drained (chunk cg - 4)
         mbar_wait_warp(&sm.acc1_empty[cg & 3], ((cg >> 2) - 1) & 1);
@@ -332,15 +398,16 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t bslot = smem_u32(sW(g % M_NB));
         const uint32_t d = tmem + (uint32_t)(M_COL_X + (cg & 3) * M_CH);
+        // k-block kk / 4: a [32 n x 32 k] sub-image (4 KB) of the unit's hi / lo image; 32-byte step kk % 4 inside its rows
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-          // k-block kk / 4: a [32 n x 32 k] sub-image (4 KB) of the unit's hi / lo image; 32-byte step kk % 4 inside its rows
-          const uint64_t dBh = make_desc(bslot + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2);
-          const uint64_t dBl = make_desc(bslot + M_TILE + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2);
-          umma_tf32_ta(d, tmem + M_COL_ALN_LO + kk * 8, dBh, idesc32, kk > 0 ? 1u : 0u);
-          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kk * 8, dBl, idesc32, 1u);
-          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kk * 8, dBh, idesc32, 1u);
-        }
+        for (int kk = 0; kk < 16; ++kk)
+          umma_tf32_ta(d, tmem + M_COL_ALN_LO + kk * 8, make_desc(bslot + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2), idesc32, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kk * 8, make_desc(bslot + M_TILE + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2), idesc32, 1u);
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk)
+          umma_tf32_ta(d, tmem + M_COL_ALN_HI + kk * 8, make_desc(bslot + (kk >> 2) * 4096) + (uint64_t)((kk & 3) * 2), idesc32, 1u);
         umma_commit(&sm.done[g % M_NB]);
         umma_commit(&sm.acc1_full[cg & 3]);
       }
@@ -348,9 +415,16 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
       mtrace(tp, g * 4 + 2);
       ++g;
     };
-    // F2 unit: the 128 fc2 rows against one hidden chunk (K = 32); A = GELU'd hidden chunk from shared memory
-    auto issue_f2 = [&](uint32_t cg, bool last_of_tile) {
+    // F2 unit: the 128 fc2 rows against one hidden chunk (K = 32); A = GELU'd hidden chunk from shared memory.  acc0 is restarted
+    // with units 0, 4, 8, 12 of a tile (the workers have moved the previous partial sum into their registers) and handed to
+    // the workers after units 3, 7, 11 (part_full) and 15 (acc0_final).
+    auto issue_f2 = [&](uint32_t cg, int c, uint32_t it) {
+      const bool fresh = (c & 3) == 0;
       mbar_wait_warp(&sm.h_full[cg & 1], (cg >> 1) & 1);
+      if (fresh && c > 0) {
+        const uint32_t d = it * 3 + (uint32_t)(c >> 2) - 1;
+        mbar_wait_warp(&sm.part_drained, d & 1);
+      }
       mtrace(tp, g * 4 + 0);
       wait_b(g);
       mtrace(tp, g * 4 + 1);
@@ -361,15 +435,15 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
         const uint32_t hbuf = smem_u32(sH + (cg & 1) * M_UNIT);
         const uint64_t dAh = make_desc(hbuf), dAl = make_desc(hbuf + M_TILE);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint64_t adv = (uint64_t)(ks * 2);
-          umma_tf32(acc0, dAl + adv, dBh + adv, idesc128, 1u);
-          umma_tf32(acc0, dAh + adv, dBl + adv, idesc128, 1u);
-          umma_tf32(acc0, dAh + adv, dBh + adv, idesc128, 1u);
-        }
+        for (int ks = 0; ks < 4; ++ks) umma_tf32(acc0, dAl + (uint64_t)(ks * 2), dBh + (uint64_t)(ks * 2), idesc128, (fresh && ks == 0) ? 0u : 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_tf32(acc0, dAh + (uint64_t)(ks * 2), dBl + (uint64_t)(ks * 2), idesc128, 1u);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) umma_tf32(acc0, dAh + (uint64_t)(ks * 2), dBh + (uint64_t)(ks * 2), idesc128, 1u);
         umma_commit(&sm.done[g % M_NB]);
         umma_commit(&sm.h_free[cg & 1]);
-        if (last_of_tile) umma_commit(&sm.acc0_final);
+        if ((c & 3) == 3 && c < M_NCH - 1) umma_commit(&sm.part_full);
+        if (c == M_NCH - 1) umma_commit(&sm.acc0_final);
       }
       __syncwarp();
       mtrace(tp, g * 4 + 2);
@@ -381,14 +455,12 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
     int it = 0;
     if (warp == M_MMA_WARP) {
       for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
-        if (it > 0) mbar_wait_warp(&sm.acc0_empty, (it - 1) & 1);         // previous tile's x has been read out of acc0
-        // ---- phase 1: acc0 (= x if the residual was preloaded) += [X | E] . W1cat^T
+        if (it > 0) mbar_wait_warp(&sm.acc0_empty, (it - 1) & 1);         // previous tile's last partial sum has been read out of acc0
+        // ---- phase 1: acc0 = [X | E] . W1cat^T  (the update only: no bias, no residual)
         g = (uint32_t)it * upt;
-        for (int kb = 0; kb < nb; ++kb, ++pu) {
+        for (int j = 0; j < n1; ++j, ++pu) {
           mtrace(tp, g * 4 + 0);
           asm volatile("bar.sync %0, %1;" ::"r"(1 + pu % 3), "r"(M_HANDOFF) : "memory");
-          if (kb < n_e) continue;                                          // a preloaded residual block: nothing to multiply
-          const int j = kb - n_e;
           mtrace(tp, g * 4 + 3);
           wait_b(g);
           mtrace(tp, g * 4 + 1);
@@ -398,12 +470,11 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
             const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + M_TILE);
             const uint32_t tAh = tmem + abuf_col(j % M_ABUF), tAl = tAh + 32;
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t adv = (uint64_t)(ks * 2);
-              umma_tf32_ta(acc0, tAl + ks * 8, dBh + adv, idesc128, (n_e > 0 || j > 0 || ks > 0) ? 1u : 0u);
-              umma_tf32_ta(acc0, tAh + ks * 8, dBl + adv, idesc128, 1u);
-              umma_tf32_ta(acc0, tAh + ks * 8, dBh + adv, idesc128, 1u);
-            }
+            for (int ks = 0; ks < 4; ++ks) umma_tf32_ta(acc0, tAl + ks * 8, dBh + (uint64_t)(ks * 2), idesc128, (j > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_tf32_ta(acc0, tAh + ks * 8, dBl + (uint64_t)(ks * 2), idesc128, 1u);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma_tf32_ta(acc0, tAh + ks * 8, dBh + (uint64_t)(ks * 2), idesc128, 1u);
             umma_commit(&sm.done[g % M_NB]);
             if (j == n1 - 1) umma_commit(&sm.p1_full);
           }
@@ -414,7 +485,7 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
         // ---- phase 3, fc2 half: F2(0..15), each as soon as its hidden chunk is in shared memory
         for (int c = 0; c < M_NCH; ++c) {
           g = (uint32_t)it * upt + pos_f2(c);
-          issue_f2(gc + c, c == M_NCH - 1);
+          issue_f2(gc + c, c, (uint32_t)it);
         }
         gc += M_NCH;
       }
@@ -460,62 +531,17 @@ mlp_chain_kernel(const nmrf_mlp_args a, int ntiles) {
       }
     }
   } else {
-    // =============================================== LN / GELU / store warps ===============================================
+    // =============================================== workers 2, 3 of every lane quarter ===============================================
     const int e = warp - M_EPI_WARP0;
     const int q = warp & 3;                    // TMEM lane quarter this warp may access
-    const int half = e >> 2;                   // two warps per quarter: columns [64 half, 64 half + 64); GELU worker 2 + half
+    const int j = 2 + (e >> 2);                // worker index: columns [32 j, 32 j + 32)
     const int row = q * 32 + lane;             // row of the tile owned by this thread
     const uint32_t t_lane = ((uint32_t)(q * 32)) << 16;
-    // store staging of the final epilogue: rows q*32..+32 of hidden buffer `half`'s hi image (4 KB); nobody writes the hidden
-    // buffers between the last fc2 of a tile and the LayerNorm of the next, which all eight of these warps must have passed
-    uint8_t* stage = sH + half * M_UNIT + q * 32 * 128;
-    const int srow = lane >> 3, sc8 = lane & 7;
-    uint32_t gc = 0;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
-      const int row0 = t * M_BM;
-      // ---- LN2 of x1 = acc0 + b_proj: worker 2 + half of the quarter ----
-      mbar_wait_warp(&sm.p1_full, it & 1);
-      mtrace(tp, 3968 + it * 8 + 0);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      ln_worker(sm, tmem + t_lane, q, row, 2 + half, lane);
-      mtrace(tp, 3968 + it * 8 + 1);
       float v[32];
-      // ---- hidden chunks: GELU workers 2 and 3 of the quarter ----
-      for (int c = 0; c < M_NCH; ++c, ++gc)
-        gelu_worker(sm, tmem + t_lane, sH, row, 2 + half, gc, sm.b1 + ((c + rot) & (M_NCH - 1)) * M_CH + (2 + half) * 8, lane, tp);
-      // ---- final: x = acc0 + (b_proj + b_fc2), columns 64 half..+64 of this warp's 32 rows, coalesced through the staging ----
-      mbar_wait_warp(&sm.acc0_final, it & 1);
-      mtrace(tp, 3968 + it * 8 + 2);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      float w[32];
-      tmem_ld32(tmem + t_lane + (uint32_t)(half * 64), v);
-      tmem_ld32(tmem + t_lane + (uint32_t)(half * 64 + 32), w);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive_m(&sm.acc0_empty);
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const float* src = ch == 0 ? v : w;
-#pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8)
-          *reinterpret_cast<float4*>(stage + swz(lane, c8)) = make_float4(src[c8 * 4], src[c8 * 4 + 1], src[c8 * 4 + 2], src[c8 * 4 + 3]);
-        __syncwarp();
-        const int n = half * 64 + ch * 32 + sc8 * 4;
-        const float4 bo = *reinterpret_cast<const float4*>(sm.bout + n);
-#pragma unroll
-        for (int i8 = 0; i8 < 8; ++i8) {
-          const int lr = i8 * 4 + srow;
-          const int r = row0 + q * 32 + lr;
-          if (r < a.rows) {
-            float4 o = *reinterpret_cast<const float4*>(stage + swz(lr, sc8));
-            o.x += bo.x; o.y += bo.y; o.z += bo.z; o.w += bo.w;
-            *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
-          }
-        }
-        __syncwarp();
-      }
-      mtrace(tp, 3968 + it * 8 + 3);
+      load_residual(a, t * M_BM + row, j, v);  // in flight during phase 1
+      worker_tile(sm, a, tmem + t_lane, sH, q, row, j, lane, it, t * M_BM + row, rot, v, tp);
     }
   }
 

@@ -20,11 +20,17 @@
 //                           4-slot ring, as soon as the MMAs that read a slot have completed (a fourth slot instead of a
 //                           fourth raw-A stage: the MMA warp waited ~300 cycles per unit for weights with three)
 //
-//   tile        128 rows x 128 output columns, unit = one k-block of 32; three accumulator stages (3 x 128 TMEM columns)
-//               so the epilogue of a tile overlaps the MMAs of the next two; A tiles double buffered (2 x 64 columns).
-//               TMEM map: [0,384) accumulators, [384,512) A: buffer b at 384 + 64 b, hi at +0, lo at +32.
-//   waiting     one lane per warp polls an mbarrier, the others park at __syncwarp (tc_common.cuh: mbar_wait_warp):
-//               32-lane spins were a third of all issued instructions and clogged the MIO queue.
+//   tile        128 rows x 128 output columns, unit = one k-block of 32; A tiles double buffered (2 x 64 columns).
+//               TMEM map: [0,384) three accumulator stages, [384,512) A: buffer b at 384 + 64 b, hi at +0, lo at +32.
+//   accumulation every GROUP of G = 2..4 units (half a tile's k-blocks) gets a fresh accumulator stage (ring of three): at
+//               most 12 G MMAs -- per k-block the eight small lo.hi / hi.lo products first, then the four hi.hi ones -- ever
+//               accumulate into the same tensor-memory columns, and the epilogue warps add the groups' partial sums in fp32
+//               registers (round-to-nearest).  The tensor core updates its accumulator with round-toward-zero
+//               (tools/precision_probe.py: relative bias -1.6e-8 per MMA, -7.7e-7 for a K = 128 product accumulated in place,
+//               5x the rms error of fp32 FMAs): summed in place, the projections were the noisiest arithmetic of the whole
+//               forward and flipped argmax / median decisions downstream.  (One stage per unit measured the same accuracy but
+//               let the MMA warp run only 3 units ahead of a tile's store phase: 84 instead of 35 us per launch.)
+//   waiting     all 32 lanes of a warp poll an mbarrier (tc_common.cuh: mbar_wait_warp): the warp stays converged.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -57,6 +63,20 @@ struct G6Smem {
   float mean[G6_STATS][G6_BM], rstd[G6_STATS][G6_BM];
   alignas(16) float gamma[128];           // LayerNorm affine (Kx == 128), staged once; read as float4
   alignas(16) float beta[128];
+};
+
+// CONV mode: the same kernel as an implicit-GEMM convolution over an NHWC image (N1 / N2 of the scope table: the k x k
+// convolutions of the feature extractor and of the conv heads; reference nmrf/models/backbone.py:48-98, NMRF.py:56-65,
+// DPN.py:45-49).  GEMM row = output pixel (n, yo, xo); k-block kb = (tap, 32-channel block): tap = kb / cpb = ky * kw + kx,
+// c0 = 32 (kb % cpb).  The raw A tile of a k-block is, per row, the 128 contiguous bytes at input pixel
+// (yo * stride - pad + ky, xo * stride - pad + kx), channel c0 -- zero-filled (cp.async src-size 0) outside the image, which
+// IS the convolution's zero padding.  Everything else (hi/lo split, MMAs, grouped accumulation, epilogue) is unchanged.
+struct ConvGeom {
+  int H, W;                  // input extent (bounds of the taps)
+  int pix_stride, row_stride;   // floats between horizontally / vertically adjacent input pixels
+  long long img_stride;      // floats between samples
+  int Ho, Wo;                // output extent: rows = N * Ho * Wo
+  int kw, stride, pad, cpb;  // kernel width, stride, padding, k-blocks (32 channels) per tap
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -105,9 +125,11 @@ __device__ __noinline__ void tile_stats6(const float* __restrict__ X, int ldx, i
 }
 
 // tile t -> (row block, 128-column chunk): column-chunk-major, so concurrently running CTAs share a weight chunk (L2)
-template <int ACT, bool LN>
+// 576 threads = 18 warps = up to 5 warps on one of the SM's four register-file partitions (16 384 registers each): at most
+// 96 registers per thread, which __launch_bounds__ makes ptxas respect (112 "fits" 65 536 / 576 but fails to launch)
+template <int ACT, bool LN, bool CONV>
 __global__ void __launch_bounds__(G6_BLOCK, 1)
-token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
+token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom cg) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   __shared__ G6Smem sm;
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
@@ -125,6 +147,9 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
   const int nkb = (Ktot + G6_BK - 1) / G6_BK;
   const int ntiles = n_rb * n_nc;
   const int tstep = gridDim.x;
+  // units per accumulator stage: half the tile's k-blocks, between 2 and 4; groups per tile
+  const int G = min(4, max(2, (nkb + 1) / 2));
+  const int ngrp = (nkb + G - 1) / G;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(512));
@@ -156,6 +181,8 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
     const float* f_x[4];       // this thread's four source rows of the fetch cursor's tile (X part, E part), refreshed per tile:
     const float* f_e[4];       // the index arithmetic (a modulo, a division by ediv) stays out of the per-unit path
     uint32_t f_ok = 0;
+    int f_yx[4];               // CONV: (yo * stride - pad) << 16 | (xo * stride - pad) & 0xffff of the four rows
+    int f_tap = 0, f_cb = 0;   // CONV: tap and channel block of the fetch cursor's k-block
     auto fetch_tile = [&]() {
       const int row0 = (f_t % n_rb) * G6_BM;
       f_ok = 0;
@@ -165,23 +192,45 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
         const bool ok = grow < a.rows;
         f_ok |= (ok ? 1u : 0u) << j;
         const int gr = ok ? grow : 0;
-        f_x[j] = a.X + (size_t)gr * a.ldx + f_c * 4;
-        f_e[j] = a.E ? a.E + (size_t)(gr / a.ediv) * a.lde + f_c * 4 - a.Kx : a.X;
+        if (CONV) {
+          const int per = cg.Ho * cg.Wo;
+          const int n = gr / per, rem = gr - n * per;
+          const int yo = rem / cg.Wo, xo = rem - yo * cg.Wo;
+          const int yi = yo * cg.stride - cg.pad, xi = xo * cg.stride - cg.pad;
+          f_yx[j] = (yi << 16) | (xi & 0xffff);
+          f_x[j] = a.X + (long long)n * cg.img_stride + (long long)yi * cg.row_stride + (long long)xi * cg.pix_stride + f_c * 4;
+          f_e[j] = a.X;
+        } else {
+          f_x[j] = a.X + (size_t)gr * a.ldx + f_c * 4;
+          f_e[j] = a.E ? a.E + (size_t)(gr / a.ediv) * a.lde + f_c * 4 - a.Kx : a.X;
+        }
       }
     };
     if (f_t < ntiles) fetch_tile();
     auto fetch_next = [&](uint32_t stage) {
       if (f_t < ntiles) {
         const uint32_t dst = smem_u32(sRaw(stage));
-        const int k0 = f_kb * G6_BK;
-        const bool in_x = k0 + f_c * 4 < a.Kx, in_k = k0 + f_c * 4 < Ktot;
+        if (CONV) {
+          const int ky = f_tap / cg.kw, kx = f_tap - ky * cg.kw;
+          const long long off = (long long)ky * cg.row_stride + (long long)kx * cg.pix_stride + f_cb * G6_BK;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool ok = in_k && ((f_ok >> j) & 1u);
-          const float* src = (in_x ? f_x[j] : f_e[j]) + k0;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(f_r + 32 * j, f_c)), "l"(ok ? src : a.X), "r"(ok ? 16 : 0));
+          for (int j = 0; j < 4; ++j) {
+            const int yi = (f_yx[j] >> 16) + ky, xi = (int)(short)(f_yx[j] & 0xffff) + kx;
+            const bool ok = ((f_ok >> j) & 1u) && (unsigned)yi < (unsigned)cg.H && (unsigned)xi < (unsigned)cg.W;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(f_r + 32 * j, f_c)), "l"(ok ? f_x[j] + off : a.X), "r"(ok ? 16 : 0));
+          }
+          if (++f_cb == cg.cpb) { f_cb = 0; ++f_tap; }
+        } else {
+          const int k0 = f_kb * G6_BK;
+          const bool in_x = k0 + f_c * 4 < a.Kx, in_k = k0 + f_c * 4 < Ktot;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool ok = in_k && ((f_ok >> j) & 1u);
+            const float* src = (in_x ? f_x[j] : f_e[j]) + k0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(f_r + 32 * j, f_c)), "l"(ok ? src : a.X), "r"(ok ? 16 : 0));
+          }
         }
-        if (++f_kb == nkb) { f_kb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
+        if (++f_kb == nkb) { f_kb = 0; f_tap = 0; f_cb = 0; f_t += tstep; if (f_t < ntiles) fetch_tile(); }
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -249,16 +298,17 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == G6_MMA_WARP) {
     // =============================================== MMA issuer ===============================================
-    uint32_t unit = 0;
+    uint32_t unit = 0, grp = 0;
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
       const int n_base = (t / n_rb) * G6_BN;
-      const int as = it % G6_ACC;
-      if (it >= G6_ACC) mbar_wait_warp(&sm.acc_empty[as], ((it / G6_ACC) - 1) & 1, 32);   // epilogue of tile it-3 has drained the stage
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t idesc = make_idesc(min(G6_BN, a.N - n_base));
       for (int kb = 0; kb < nkb; ++kb, ++unit) {
         const int slot = unit % G6_NB;
+        const int as = grp % G6_ACC;            // accumulator stage of this group of units
+        const bool first = kb % G == 0, last = (kb % G == G - 1) || kb == nkb - 1;
+        if (first && grp >= G6_ACC) mbar_wait_warp(&sm.acc_empty[as], ((grp / G6_ACC) - 1) & 1);   // the epilogue has drained group - 3
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         trace(tp, 2048 + unit * 4 + 0);
         asm volatile("bar.sync %0, %1;" ::"r"(1 + slot), "r"(G6_HANDOFF) : "memory");      // A of this unit is in TMEM
         trace(tp, 2048 + unit * 4 + 3);
@@ -269,17 +319,18 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
           const uint64_t dBh = make_desc(smem_u32(sB_hi(slot))), dBl = make_desc(smem_u32(sB_lo(slot)));
           const uint32_t d = tmem + (uint32_t)(as * G6_BN);
           const uint32_t tAh = tmem + (uint32_t)(G6_ACOL + (unit & 1) * 64), tAl = tAh + 32;
+          // k-step ks: B +32 bytes inside the swizzle row, A +8 TMEM columns.  Small products first (fresh accumulator).
 #pragma unroll
-          for (int ks = 0; ks < G6_BK / 8; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 2);               // B: +32 bytes inside the swizzle row; A: +8 TMEM columns
-            umma_tf32_ta(d, tAl + ks * 8, dBh + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            umma_tf32_ta(d, tAh + ks * 8, dBl + adv, idesc, 1u);
-            umma_tf32_ta(d, tAh + ks * 8, dBh + adv, idesc, 1u);
-          }
+          for (int ks = 0; ks < G6_BK / 8; ++ks) umma_tf32_ta(d, tAl + ks * 8, dBh + (uint64_t)(ks * 2), idesc, (ks > 0 || !first) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < G6_BK / 8; ++ks) umma_tf32_ta(d, tAh + ks * 8, dBl + (uint64_t)(ks * 2), idesc, 1u);
+#pragma unroll
+          for (int ks = 0; ks < G6_BK / 8; ++ks) umma_tf32_ta(d, tAh + ks * 8, dBh + (uint64_t)(ks * 2), idesc, 1u);
           umma_commit(&sm.done[slot]);
-          if (kb == nkb - 1) umma_commit(&sm.acc_full[as]);
+          if (last) umma_commit(&sm.acc_full[as]);
         }
         __syncwarp();
+        if (last) ++grp;
         trace(tp, 2048 + unit * 4 + 2);
       }
     }
@@ -320,19 +371,46 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
     };
     if (LN) { stats(0); stats(1); stats(2); }
     int it = 0;
+    uint32_t grp = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
       const int row0 = (t % n_rb) * G6_BM, n_base = (t / n_rb) * G6_BN;
-      const int as = it % G6_ACC;
       // buffer (it+3) % 4 last held tile it-1, whose statistics the producers read before its MMAs, which this warp drained
       if (LN) stats(it + 3);
       trace(tp, 3584 + it * 4 + 0);
-      mbar_wait_warp(&sm.acc_full[as], (it / G6_ACC) & 1, 64);
-      trace(tp, 3584 + it * 4 + 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int nchunks = (min(G6_BN, a.N - n_base) + 31) / 32;
-      for (int ch = half; ch < nchunks; ch += 2) {
-        float v[32];
-        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G6_BN + ch * 32), v);
+      // the tile's sum over its groups of k-blocks, in registers: this thread's row, column chunks half and half + 2 (32 columns each)
+      float acc[2][32];
+      for (int kb = 0; kb < ngrp; ++kb, ++grp) {
+        const int as = grp % G6_ACC;
+        mbar_wait_warp(&sm.acc_full[as], (grp / G6_ACC) & 1, kb == 0 ? 64 : 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int ch = half + 2 * ci;
+          if (ch < nchunks) {
+#pragma unroll
+            for (int h16 = 0; h16 < 2; ++h16) {      // 16 columns at a time: the 64 accumulator registers stay live
+              float v[16];
+              tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * G6_BN + ch * 32 + h16 * 16), v);
+              if (kb == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[ci][h16 * 16 + j] = v[j];
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[ci][h16 * 16 + j] += v[j];
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(&sm.acc_empty[as]);
+      }
+      trace(tp, 3584 + it * 4 + 1);
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci) {
+        const int ch = half + 2 * ci;
+        if (ch >= nchunks) break;
+        const float* v = acc[ci];
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -341,29 +419,30 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc) {
         if (n < a.N) {
           float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
           if (a.bias) b = *reinterpret_cast<const float4*>(a.bias + n);
-          float4 rr[8];                         // residual first (R may alias Y: read-before-write by the same thread)
+#pragma unroll 1
+          for (int g4 = 0; g4 < 2; ++g4) {      // four rows per lane at a time: the other chunk's 32 accumulator registers are live
+            float4 rr[4];                       // residual first (R may alias Y: read-before-write by the same thread)
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int r = row0 + q * 32 + i8 * 4 + srow;
-            rr[i8] = (a.R && r < a.rows) ? __ldcg(reinterpret_cast<const float4*>(a.R + (size_t)r * a.ldr + n))
-                                         : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int r = row0 + q * 32 + (g4 * 4 + i4) * 4 + srow;
+              rr[i4] = (a.R && r < a.rows) ? __ldcg(reinterpret_cast<const float4*>(a.R + (size_t)r * a.ldr + n))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            const int lr = i8 * 4 + srow;
-            const int r = row0 + q * 32 + lr;
-            if (r < a.rows) {
-              float4 o = *reinterpret_cast<const float4*>(stage + lr * 36 + scol);
-              o.x = act_fast(o.x + b.x, ACT) + rr[i8].x; o.y = act_fast(o.y + b.y, ACT) + rr[i8].y;
-              o.z = act_fast(o.z + b.z, ACT) + rr[i8].z; o.w = act_fast(o.w + b.w, ACT) + rr[i8].w;
-              *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const int lr = (g4 * 4 + i4) * 4 + srow;
+              const int r = row0 + q * 32 + lr;
+              if (r < a.rows) {
+                float4 o = *reinterpret_cast<const float4*>(stage + lr * 36 + scol);
+                o.x = act_fast(o.x + b.x, ACT) + rr[i4].x; o.y = act_fast(o.y + b.y, ACT) + rr[i4].y;
+                o.z = act_fast(o.z + b.z, ACT) + rr[i4].z; o.w = act_fast(o.w + b.w, ACT) + rr[i4].w;
+                *reinterpret_cast<float4*>(a.Y + (size_t)r * a.ldy + n) = o;
+              }
             }
           }
         }
         __syncwarp();
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(&sm.acc_empty[as]);
       trace(tp, 3584 + it * 4 + 2);
     }
   }
@@ -430,11 +509,11 @@ int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t s
 }
 
 namespace {
-template <int ACT, bool LN>
-void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t stream) {
+template <int ACT, bool LN, bool CONV = false>
+void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
   static PerDevice configured;        // per instantiation and device
-  ensure_dynamic_smem(token_gemm_tc6_kernel<ACT, LN>, G6_DYN, configured);
-  token_gemm_tc6_kernel<ACT, LN><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc);
+  ensure_dynamic_smem(token_gemm_tc6_kernel<ACT, LN, CONV>, G6_DYN, configured);
+  token_gemm_tc6_kernel<ACT, LN, CONV><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc, cg);
 }
 }  // namespace
 
@@ -457,6 +536,34 @@ int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream) {
   }
   count_launch();
   return check_launch("token_gemm_tc6");
+}
+
+// N1 / N2: k x k convolution over NHWC as an implicit GEMM on the kernel above (CONV mode)
+int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream) {
+  NMRF_REQUIRE(c.X && c.Wt_hi && c.Wt_lo && c.Y, "conv2d: null pointer");
+  NMRF_REQUIRE(c.N > 0 && c.H > 0 && c.W > 0 && c.kh > 0 && c.kw > 0 && c.stride > 0 && c.pad >= 0, "conv2d: bad geometry");
+  NMRF_REQUIRE(c.Cin > 0 && c.Cin % 32 == 0, "conv2d: Cin=%d must be a multiple of 32 (floats consumed per tap)", c.Cin);
+  NMRF_REQUIRE(c.Cout > 0 && c.Cout % 16 == 0, "conv2d: Cout=%d must be a multiple of 16", c.Cout);
+  NMRF_REQUIRE(c.pix_stride % 4 == 0 && c.row_stride % 4 == 0 && c.img_stride % 4 == 0, "conv2d: strides must keep 16-byte alignment");
+  NMRF_REQUIRE(c.H < 32768 && c.W < 32768, "conv2d: image extent above 32767");
+  const int Ho = c.Ho > 0 ? c.Ho : (c.H + 2 * c.pad - c.kh) / c.stride + 1, Wo = c.Wo > 0 ? c.Wo : (c.W + 2 * c.pad - c.kw) / c.stride + 1;
+  NMRF_REQUIRE(Ho > 0 && Wo > 0 && (long long)c.N * Ho * Wo < (1ll << 31), "conv2d: bad output extent %dx%d", Ho, Wo);
+  nmrf_gemm_args a = {};
+  a.X = c.X; a.Kx = c.kh * c.kw * c.Cin; a.ldx = 0;
+  a.ediv = 1;
+  a.bias = c.bias;
+  a.Y = c.Y; a.ldy = c.Cout;
+  a.rows = c.N * Ho * Wo; a.N = c.Cout;
+  a.Wt_hi = c.Wt_hi; a.Wt_lo = c.Wt_lo;
+  ConvGeom g;
+  g.H = c.H; g.W = c.W; g.pix_stride = c.pix_stride; g.row_stride = c.row_stride; g.img_stride = c.img_stride;
+  g.Ho = Ho; g.Wo = Wo; g.kw = c.kw; g.stride = c.stride; g.pad = c.pad; g.cpb = c.Cin / 32;
+  const int num_sms = nmrf::num_sms();
+  const int n_rb = (a.rows + G6_BM - 1) / G6_BM, n_nc = (a.N + G6_BN - 1) / G6_BN;
+  const int ntiles = n_rb * n_nc;
+  launch6<0, false, true>(a, n_rb, n_nc, ntiles < num_sms ? ntiles : num_sms, stream, g);
+  count_launch();
+  return check_launch("conv2d");
 }
 
 }  // namespace nmrf

@@ -194,9 +194,9 @@ class _Launches:
 
     def block_tail(self, what, att, x, rows, proj_w, proj_b, n2, fc1_w, fc1_b, fc2_w, fc2_b):
         """x = x1 + Mlp(LN2(x1)), x1 = x + proj(att): ONE launch of nmrf_mlp_chain (SwinNMP / CSWinNMP tail, NMP.py:358-363,
-        570-573).  The residual stream x is written into the fp32 accumulator before the MMAs (exact add, four weight units
-        less per tile: 71 vs 73 us per launch on the same GPU); NMRF_B200_RESIDUAL=identity lets it ride the tensor core as an
-        identity block appended to the proj weight instead (error <= 2^-22 |x|, like every other 3xTF32 product)."""
+        570-573).  The residual stream x stays in fp32 registers inside the kernel (gemm_mlp.cu: never in a tensor-core
+        accumulator, whose round-toward-zero updates would bias it); NMRF_B200_RESIDUAL=identity (experiment) lets it ride the
+        tensor core as an identity block appended to the proj weight instead."""
         from . import ops
         key = (proj_w.data_ptr(), fc1_w.data_ptr(), fc2_w.data_ptr())
         if key not in self._streams:
@@ -205,7 +205,7 @@ class _Launches:
             else:
                 w1 = torch.cat([proj_w, torch.eye(128, device=proj_w.device, dtype=torch.float32)], 1).contiguous()
             ws = ops.pack_mlp_stream(w1, fc1_w.contiguous(), fc2_w.contiguous())
-            self._streams[key] = (ws, (proj_b + fc2_b).contiguous())
+            self._streams[key] = (ws, fc2_b.contiguous())
         ws, bias_out = self._streams[key]
         a = MlpArgs()
         a.X, a.ldx, a.Kx = att.data_ptr(), att.stride(0), 128

@@ -212,7 +212,7 @@ class NMRF(nn.Module):
         self.register_buffer("device_indicator_tensor", torch.empty(0))
         self._packed = None
         self._plans = {}
-        self.cudnn_benchmark = False      # let cuDNN autotune the (out-of-path) fp32 convolutions
+        self.cudnn_benchmark = False      # module path only (foreign encoders): let cuDNN autotune its convolutions
         # out-of-path torch convolutions: "3xtf32" = fp32-accurate on TF32 tensor cores (exactconv.py),
         # "fp32" = cuDNN with TF32 disabled (slow on B200), "tf32" = cuDNN default (fast, breaks parity)
         self.conv_mode = "3xtf32"
@@ -274,6 +274,8 @@ class NMRF(nn.Module):
 
     @torch.no_grad()
     def forward_device(self, img1, img2):
+        if self.device.type != "cuda":
+            raise RuntimeError("nmrf_b200.NMRF runs on CUDA only (there is no CPU path); call .cuda() first")
         # everything below launches on the MODEL's device: weight packing, the encoder and the plan make it current
         # (the library configures its kernels per device and launches on the current one)
         with torch.cuda.device(self.device):
@@ -283,21 +285,21 @@ class NMRF(nn.Module):
         B, _, H, W = img1.shape
         d = self.divis_by                                          # frame_utils.py:264-269 ('proposal' mode)
         pad_h, pad_w = (((H // d) + 1) * d - H) % d, (((W // d) + 1) * d - W) % d
+        if (self.fused_encoder and self.compat and self.conv_mode == "3xtf32" and type(self.backbone) is Backbone
+                and isinstance(self.backbone.norm1, nn.InstanceNorm2d)):      # the fused encoder computes InstanceNorm only
+            Hp_, Wp_ = H + pad_h, W + pad_w                        # the replicate pad happens inside nmrf_image_prep
+            h8, w8 = Hp_ // 8, Wp_ // 8
+            plan = self.plan_for(B, self.backbone.output_dim, h8, w8, H, W)
+            if self._encoder is None:
+                self._encoder = FusedEncoder(self)
+            self._encoder.run(img1, img2, plan, (Hp_, Wp_))
+            plan.run()
+            return self._outputs(plan, B)
         if pad_h or pad_w:
             img1 = F.pad(img1, [0, pad_w, 0, pad_h], mode="replicate")
             img2 = F.pad(img2, [0, pad_w, 0, pad_h], mode="replicate")
         img1 = img1.contiguous(memory_format=torch.channels_last)
         img2 = img2.contiguous(memory_format=torch.channels_last)
-        if (self.fused_encoder and self.compat and self.conv_mode == "3xtf32" and type(self.backbone) is Backbone
-                and isinstance(self.backbone.norm1, nn.InstanceNorm2d)):      # the fused encoder computes InstanceNorm only
-            Hp_, Wp_ = img1.shape[-2:]
-            h8, w8 = Hp_ // 8, Wp_ // 8
-            plan = self.plan_for(B, self.backbone.output_dim, h8, w8, H, W)
-            if self._encoder is None:
-                self._encoder = FusedEncoder(self)
-            self._encoder.run(img1, img2, plan)
-            plan.run()
-            return self._outputs(plan, B)
         # exact-fp32 convolutions: cuDNN's default TF32 moves the features by ~5e-4 relative, which flips
         # top-K / argmax decisions downstream (EPE 0.2-0.4 px measured) -- same reason as DESIGN.md §3
         self._conv_cache.enabled = self.conv_mode == "3xtf32"
@@ -320,28 +322,6 @@ class NMRF(nn.Module):
                 gw[0].copy_(g[:B]); gw[1].copy_(g[B:])
         plan.run()
         return self._outputs(plan, B)
-
-    @torch.no_grad()
-    def autotune_encoder(self, img1, img2):
-        """Verified cuDNN autotuning of the fused encoder's convolutions for this input shape (FusedEncoder.autotune)."""
-        self.forward_device(img1, img2)                                # builds the plan and the encoder
-        if self._encoder is None:
-            return None
-        with torch.cuda.device(self.device):
-            return self._autotune_encoder(img1, img2)
-
-    def _autotune_encoder(self, img1, img2):
-        B, _, H, W = img1.shape
-        d = self.divis_by
-        pad_h, pad_w = (((H // d) + 1) * d - H) % d, (((W // d) + 1) * d - W) % d
-        if pad_h or pad_w:
-            img1 = F.pad(img1, [0, pad_w, 0, pad_h], mode="replicate")
-            img2 = F.pad(img2, [0, pad_w, 0, pad_h], mode="replicate")
-        img1 = img1.contiguous(memory_format=torch.channels_last)
-        img2 = img2.contiguous(memory_format=torch.channels_last)
-        Hp_, Wp_ = img1.shape[-2:]
-        plan = self.plan_for(B, self.backbone.output_dim, Hp_ // 8, Wp_ // 8, H, W)
-        return self._encoder.autotune(img1, img2, plan)
 
     def _outputs(self, plan, B):
         K = self.num_proposals

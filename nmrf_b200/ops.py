@@ -120,8 +120,8 @@ def pack_mlp_stream(W1cat, Wfc1, Wfc2):
 
 @_on_device
 def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_identity=False):
-    """Y = x1 + fc2(GELU(fc1(LN(x1)))) + b_fc2 (bias_out = bias_mid + b_fc2) with x1 = X @ W1.T + bias_mid + E (e_identity: E is the
-    residual, added exactly) or x1 = concat(X, E) @ W1cat.T + bias_mid; wstream from pack_mlp_stream(W1 or W1cat, ...).
+    """Y = x1 + (fc2(GELU(fc1(LN(x1)))) + bias_out) (bias_out = b_fc2) with x1 = E + (X @ W1.T + bias_mid) (e_identity: E is the
+    residual, kept in fp32 registers) or x1 = concat(X, E) @ W1cat.T + bias_mid; wstream from pack_mlp_stream(W1 or W1cat, ...).
     `out` may alias E."""
     for n, t in (("X", X), ("E", E), ("wstream", wstream), ("bias_mid", bias_mid), ("gamma", ln[0]), ("beta", ln[1]), ("b1", b1),
                  ("bias_out", bias_out)):

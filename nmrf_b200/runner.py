@@ -1,29 +1,22 @@
-"""CUDA-graph runner: the whole forward (torch feature extractor + libnmrf_b200 hot path) captured once
-per input shape and replayed, so a step costs one graph launch instead of ~150 kernel launches."""
+"""CUDA-graph runner: the whole forward (feature extractor + hot path, every launch a libnmrf_b200 kernel) captured once
+per input shape and replayed, so a step costs one graph launch instead of ~200 kernel launches."""
 import torch
 
 
 class GraphedNMRF:
     """`runner(img1, img2)`: images may live on the host (pinned memory recommended) or on the device."""
 
-    def __init__(self, model, B, H, W, warmup=3, autotune_convs=False, tune_images=None):
+    def __init__(self, model, B, H, W, warmup=3):
         assert model.device.type == "cuda"
         self.model = model
         dev = model.device
         self.img1 = torch.zeros(B, 3, H, W, device=dev)
         self.img2 = torch.zeros(B, 3, H, W, device=dev)
-        self.autotune_report = None
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):                       # builds the plan, sets kernel attributes, warms cuDNN
                 model.forward_device(self.img1, self.img2)
-            if autotune_convs and getattr(model, "_encoder", None) is not None:
-                # verified cuDNN autotuning of the encoder's convolutions (encoder.py: autotune), on real-looking images
-                a, b = tune_images if tune_images is not None else (torch.rand_like(self.img1) * 255, torch.rand_like(self.img2) * 255)
-                self.autotune_report = model.autotune_encoder(a.to(dev), b.to(dev))
-                for _ in range(2):
-                    model.forward_device(self.img1, self.img2)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.graph = torch.cuda.CUDAGraph()

@@ -421,6 +421,8 @@ def hot_path(sd, cfg, f1_list, f2_list):
 
     fc1, fc2 = conv_head(sd, "concatconv", f1_8), conv_head(sd, "concatconv", f2_8)
     fg1, fg2 = conv_head(sd, "gw", f1_8), conv_head(sd, "gw", f2_8)
+    if taps is not None:
+        taps.update(f8=(f1_8, f2_8), cc8=(fc1, fc2), gw8=(fg1, fg2))
     tgt = mrf_stack(sd, cfg, "inference", labels.reshape(B, h8, w8, K), fc1, fc2, fg1, fg2,
                     cfg.num_infer_layers, cfg.window_size, 3.14 / 64, True)
     coarse, score, sel, disp_curr = infer_select(sd, tgt, labels, B, h8, w8)
@@ -431,6 +433,8 @@ def hot_path(sd, cfg, f1_list, f2_list):
     fc1, fc2 = conv_head(sd, "concatconv", f1_4), conv_head(sd, "concatconv", f2_4)
     fg1, fg2 = conv_head(sd, "gw", f1_4), conv_head(sd, "gw", f2_4)
     h4, w4 = f1_4.shape[-2:]
+    if taps is not None:
+        taps.update(cc4=(fc1, fc2), gw4=(fg1, fg2))
     tgt = mrf_stack(sd, cfg, "refinement", disp_curr[..., None], fc1, fc2, fg1, fg2,
                     cfg.num_refine_layers, cfg.refine_window_size, 3.14 / 128, False)
     delta = _mlp_relu(sd, "refine_head", tgt.squeeze(1)).reshape(B, h4, w4, 4, 4)   # NMRF.py:238-242
@@ -506,3 +510,34 @@ def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations,
             acc = acc + g * (wt * ok)[..., None]
         out = out + (acc * attention_weights[:, :, :, l][..., None]).sum(3)
     return out.reshape(N, Lq, M * Dh)
+
+
+# --------------------------------------------------------------------------------------
+# N4  evaluation metrics and the KITTI writer's encoding
+#     (nmrf/utils/evaluation.py:326-359, 398-407; nmrf/utils/frame_utils.py:237-239)
+# --------------------------------------------------------------------------------------
+@torch.no_grad()
+def disp_metrics(disp_pr, disp_gt, valid_gt, only_valid, max_disp, thres):
+    """DispEvaluator.process + evaluate for a batch [B,H,W]: per-image epe / d1 / bad-t over the valid pixels (images
+    without valid pixels skipped), then the mean over images; d1 and bad-t in percent."""
+    epes, d1s, bads = [], [], {t: [] for t in thres}
+    for pr, gt, vg in zip(disp_pr, disp_gt, valid_gt):
+        valid = (vg & (gt < max_disp)) if only_valid else (gt < max_disp)
+        epe = torch.abs(pr - gt).flatten()
+        val = valid.flatten()
+        if not bool(val.any()):
+            continue
+        epes.append(epe[val].mean().item())
+        d1s.append(((epe[val] > 3) & (epe[val] / gt.flatten()[val] > 0.05)).float().mean().item())
+        for t in thres:
+            bads[t].append((epe > float(t))[val].float().mean().item())
+    res = {"epe": torch.tensor(epes).mean().item(), "d1": torch.tensor(d1s).mean().item() * 100}
+    for t in thres:
+        res[f"bad {t}"] = torch.tensor(bads[t]).mean().item() * 100
+    return res
+
+
+def kitti_u16(disp):
+    """writeDispKITTI's encoding: np.round(disp * 256).astype(np.uint16)"""
+    import numpy as np
+    return np.round(disp.cpu().numpy() * 256).astype(np.uint16)

@@ -70,11 +70,23 @@ def truth_forward(sd, max_disp, K, L, img1, img2, device=None):
     from oracle import nmrf_oracle as O
     cfg = oracle_cfg(max_disp, K, L)
     out = O.forward(O.to_float64(sd, device), cfg, img1, img2)
-    cpu = lambda d: {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in d.items()}
+    one = lambda v: v.cpu() if torch.is_tensor(v) else tuple(one(x) for x in v) if isinstance(v, tuple) else v
+    cpu = lambda d: {k: one(v) for k, v in d.items()}
     return cpu(out), cpu(cfg.taps)
 
 
-def parity_metrics(model, sd, max_disp, K, L, img1, img2):
+def load_truth_features(plan, tt):
+    """EXPERIMENT: overwrite the hot path's inputs with the float64 oracle's feature maps (rounded to fp32), so that the
+    hot path's own arithmetic is measured without the encoder's"""
+    nhwc = lambda t: t.permute(0, 2, 3, 1).float().contiguous()
+    plan.f1_8.copy_(nhwc(tt["f8"][0])); plan.f2_8.copy_(nhwc(tt["f8"][1]))
+    plan.context.copy_(tt["context"].float())
+    for name in ("cc8", "gw8", "cc4", "gw4"):
+        for i in range(2):
+            getattr(plan, name)[i].copy_(nhwc(tt[name][i]))
+
+
+def parity_metrics(model, sd, max_disp, K, L, img1, img2, truth_features=False):
     """The CUDA path AND the fp32 reference arithmetic (CPU oracle, fp32) against FLOAT64 truth on the same inputs.
 
     Why float64 truth: the reference's own fp32 forward is ~1e-3 px (EPE) away from exact arithmetic at these weights, because
@@ -90,9 +102,13 @@ def parity_metrics(model, sd, max_disp, K, L, img1, img2):
     B, _, H, W = img1.shape
     out = model({"img1": img1, "img2": img2})              # builds the plan, fills its input buffers
     plan = model.plan_for(B, plan_C(model), *feat_hw(model, H, W), H, W)
-    taps = {k: v.cpu() for k, v in plan.run_with_taps().items()}
     dev = model.device if model.device.type == "cuda" else None
     t_out, tt = truth_forward(sd, max_disp, K, L, img1, img2, dev)
+    if truth_features:
+        load_truth_features(plan, tt)
+    taps = {k: v.cpu() for k, v in plan.run_with_taps().items()}
+    if truth_features:
+        out = dict(out, disp=taps["disp"], proposal=taps["labels"].reshape(B, -1, K))
     ocfg = oracle_cfg(max_disp, K, L)
     r_out = O.forward(sd, ocfg, img1, img2)                # the reference arithmetic: torch CPU fp32
     rt = ocfg.taps

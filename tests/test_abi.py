@@ -64,7 +64,8 @@ def test_struct_field_offsets_match_a_c_compiler(tmp_path):
     if shutil.which("gcc") is None:
         import pytest
         pytest.skip("no gcc")
-    structs = {"nmrf_gemm_args": _lib.GemmArgs, "nmrf_mlp_args": _lib.MlpArgs, "nmrf_seed_weights": _lib.SeedWeights}
+    structs = {"nmrf_gemm_args": _lib.GemmArgs, "nmrf_mlp_args": _lib.MlpArgs, "nmrf_seed_weights": _lib.SeedWeights,
+               "nmrf_conv_args": _lib.ConvArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{os.path.join(ROOT, "include", "nmrf_b200.h")}"', 'int main(void) {']
     for cname, ct in structs.items():
         lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')

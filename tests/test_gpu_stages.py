@@ -116,7 +116,7 @@ def test_mlp_chain(ops, rows, mode):
     ref = x1 + torch.nn.functional.gelu(t @ W1.double().T + b1.double()) @ W2.double().T + b2.double()
     ws = ops.pack_mlp_stream(cuda(W1cat), cuda(W1), cuda(W2))
     xe = cuda(E) if E is not None else None
-    args = (cuda(X), ws, cuda(bmid), (cuda(gam), cuda(bet)), cuda(b1), cuda(bmid + b2))
+    args = (cuda(X), ws, cuda(bmid), (cuda(gam), cuda(bet)), cuda(b1), cuda(b2))
     out = ops.mlp_chain(*args, E=xe, e_identity=ident)
     assert rel_err(out, ref) <= 1e-5         # three chained 3xTF32 GEMMs (4e-6 each) + LN + GELU
     if mode == "residual":                                      # in place on the residual stream, as the hot path runs it
@@ -366,7 +366,7 @@ def test_warp_corr_embed_extended_labels(ops):
     assert rel_err(inner, ref) <= 1e-6
     ref_enc = O.fourier_embed(lab64, norm)
     got = enc.cpu().reshape(B, Hp, Wp, K, 32)[:, top:top + h, left:left + w, :, :31]
-    assert float((got.double() - ref_enc).abs().max()) <= 1e-7         # fp32 storage rounding only, at every frequency
+    assert float((got.double() - ref_enc).abs().max()) <= 2.5e-7       # fp32 storage rounding only (values up to ~2.3), at every frequency
     # the plain fp32 path (labels_lo = NULL) cannot do that: one ulp of the label is ~1e-3 rad at 2^14
     _, enc32 = ops.warp_corr_embed(nh(cc1), nh(cc2), nh(gw1), nh(gw2), cuda(hi.reshape(-1, K)), K, Hp, Wp, top, left, norm)
     got32 = enc32.cpu().reshape(B, Hp, Wp, K, 32)[:, top:top + h, left:left + w, :, :31]
@@ -392,7 +392,7 @@ def test_select_median_and_refine_tail_extended(ops):
                                             value=float("nan")).reshape(-1, 64)
     dc, dc_lo = ops.select_median(cuda(pad(delta)), cuda(pad(score)), cuda(hi), B, h, w, K, Hp, Wp, top, left, labels_lo=cuda(lo))
     ext = dc.cpu().double() + dc_lo.cpu().double()
-    assert float((ext - ref).abs().max()) <= 1e-12                    # the double sum, carried exactly as hi + lo
+    assert float((ext - ref).abs().max()) <= 1e-11                    # the double sum, carried as hi + lo (48 bits)
     assert torch.equal(dc.cpu(), ref.float())
     # refine tail on the extended disp_curr
     h4, w4, H, W = 2 * h, 2 * w, 8 * h - 3, 8 * w - 5
@@ -465,29 +465,82 @@ def test_instnorm_kernels(ops, N, H, W, C):
     s = torch.cuda.current_stream().cuda_stream
     _lib.check(_lib.lib.nmrf_instnorm_stats(x.data_ptr(), N, H * W, C, sx.data_ptr(), s), "stats")
     _lib.check(_lib.lib.nmrf_instnorm_stats(r.data_ptr(), N, H * W, C, sr.data_ptr(), s), "stats")
-    plain, cat3 = torch.empty_like(x), torch.empty(N, H, W, 3 * C, device="cuda")
+    plain = torch.empty_like(x)
     _lib.check(_lib.lib.nmrf_instnorm_apply(x.data_ptr(), sx.data_ptr(), r.data_ptr(), sr.data_ptr(), N, H * W, C, 1, 1,
-                                            plain.data_ptr(), cat3.data_ptr(), s), "apply")
+                                            plain.data_ptr(), s), "apply")
     nchw = lambda t: t.permute(0, 3, 1, 2).double()
     ref = F.relu(F.relu(F.instance_norm(nchw(x))) + F.instance_norm(nchw(r))).permute(0, 2, 3, 1)
     assert rel_err(plain, ref) <= 2e-6
-    hi, lo = cat3[..., :C], cat3[..., C:2 * C]
-    assert torch.equal(cat3[..., 2 * C:], hi)
-    assert torch.equal((hi.view(torch.int32) & 0x1FFF), torch.zeros_like(hi, dtype=torch.int32))    # tf32-representable
-    assert rel_err(hi.double() + lo.double(), plain) <= 1e-6
     # plain residual, no norm on it, inner relu only
     _lib.check(_lib.lib.nmrf_instnorm_apply(x.data_ptr(), sx.data_ptr(), r.data_ptr(), None, N, H * W, C, 1, 0,
-                                            plain.data_ptr(), None, s), "apply")
+                                            plain.data_ptr(), s), "apply")
     ref = (F.relu(F.instance_norm(nchw(x))) + nchw(r)).permute(0, 2, 3, 1)
     assert rel_err(plain, ref) <= 2e-6
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 40, 72)])
-def test_fused_encoder_matches_module_path(B, H, W):
-    """encoder.FusedEncoder (NHWC, fused glue, one cuDNN call per conv) against the torch modules run with the
-    3xTF32 convolution wrapper: the hot path's inputs must agree to fp32 rounding"""
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad", [
+    (2, 17, 23, 64, 64, 3, 1, 1), (1, 20, 31, 64, 96, 3, 2, 1), (2, 9, 12, 128, 384, 3, 1, 1), (1, 12, 16, 64, 96, 1, 2, 0),
+    (1, 6, 7, 256, 320, 3, 1, 1), (3, 5, 40, 96, 128, 1, 1, 0)])
+def test_conv2d_against_float64(N, H, W, Cin, Cout, k, stride, pad):
+    """nmrf_conv2d (implicit GEMM on tcgen05, 3xTF32, grouped accumulation) against torch's float64 convolution; the fp32
+    convolution of the reference arithmetic (torch CPU) is the yardstick: ours must not be noisier"""
+    import torch.nn.functional as F
+    from nmrf_b200.encoder import _Conv
+    g = torch.Generator().manual_seed(Cin + Cout + H)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cout * k * k)) ** 0.5
+    ref = F.conv2d(x.double(), w.double(), None, stride, pad)
+    conv = _Conv(w.cuda(), stride, pad)
+    Ho, Wo = conv.out_hw(H, W)
+    assert (Ho, Wo) == tuple(ref.shape[-2:])
+    y = torch.empty(N, Ho, Wo, Cout, device="cuda")
+    conv(cuda(x.permute(0, 2, 3, 1)), y)
+    rms = lambda a: float(((a.double().cpu() - ref) ** 2).mean().sqrt() / (ref ** 2).mean().sqrt())
+    ours, fp32 = rms(y.permute(0, 3, 1, 2)), rms(F.conv2d(x, w, None, stride, pad))
+    assert rel_err(y.permute(0, 3, 1, 2), ref) <= 2e-6
+    assert ours <= max(1.5 * fp32, 2e-7), (ours, fp32)
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 40, 72), (1, 100, 180)])
+def test_fused_encoder_against_float64_oracle(B, H, W):
+    """encoder.FusedEncoder (image_prep incl. replicate padding, stem + residual stages + heads on nmrf_conv2d, InstanceNorm
+    glue) against the oracle's feature extractor in float64; the fp32 oracle (reference arithmetic) is the yardstick"""
     from helpers import build_product_model
     from nmrf_b200.synthetic import synthetic_pair
+    model, sd = build_product_model(64, 2, (1, 1, 1), 0, "reference")
+    model = model.cuda()
+    img1, img2 = synthetic_pair(B, H, W, 64, index=1)
+    model.forward_device(img1.cuda(), img2.cuda())
+    Hp, Wp = (H + 7) // 8 * 8, (W + 7) // 8 * 8
+    plan = model.plan_for(B, 256, Hp // 8, Wp // 8, H, W)
+
+    def feats(sd_, dt):
+        both = torch.cat([O.pad_images(img1.to(dt), 8)[0], O.pad_images(img2.to(dt), 8)[0]], 0)
+        f4, f8 = O.backbone_resnet(sd_, "backbone", both)
+        out = {"f1_8": f8[:B], "f2_8": f8[B:], "context": O.conv_head(sd_, "dpn.proj", f8[:B])}
+        for s, f in ((8, f8), (4, f4)):
+            c, g_ = O.conv_head(sd_, "concatconv", f), O.conv_head(sd_, "gw", f)
+            out.update({f"cc{s}0": c[:B], f"cc{s}1": c[B:], f"gw{s}0": g_[:B], f"gw{s}1": g_[B:]})
+        return {k: v.permute(0, 2, 3, 1) for k, v in out.items()}
+    t64, t32 = feats(O.to_float64(sd), torch.float64), feats(sd, torch.float32)
+    got = {"f1_8": plan.f1_8, "f2_8": plan.f2_8, "context": plan.context}
+    for s in (8, 4):
+        for i in range(2):
+            got[f"cc{s}{i}"] = getattr(plan, f"cc{s}")[i]
+            got[f"gw{s}{i}"] = getattr(plan, f"gw{s}")[i]
+    rms = lambda a, b: float(((a.double().cpu() - b) ** 2).mean().sqrt() / (b ** 2).mean().sqrt())
+    for k in t64:
+        ours, fp32 = rms(got[k], t64[k]), rms(t32[k], t64[k])
+        assert rel_err(got[k], t64[k]) <= 1e-5, k
+        assert ours <= max(2.0 * fp32, 5e-7), (k, ours, fp32)
+
+
+def test_module_path_for_foreign_encoders_agrees_with_fused_encoder():
+    """the torch-module path (any encoder with the reference's return convention, convolutions through exactconv's cuDNN
+    3xTF32 wrapper) fills the same buffers; agreement to that wrapper's accuracy"""
+    from helpers import build_product_model
+    from nmrf_b200.synthetic import synthetic_pair
+    B, H, W = 1, 64, 96
     model, _ = build_product_model(64, 2, (1, 1, 1), 0, "reference")
     model = model.cuda()
     img1, img2 = (t.cuda() for t in synthetic_pair(B, H, W, 64, index=1))
@@ -499,4 +552,4 @@ def test_fused_encoder_matches_module_path(B, H, W):
         plan = model.plan_for(B, 256, H // 8, W // 8, H, W)
         outs[fused] = [getattr(plan, n).clone() for n in names] + [t.clone() for t in plan.cc8 + plan.gw8 + plan.cc4 + plan.gw4]
     for a, b in zip(outs[True], outs[False]):
-        assert rel_err(a, b) <= 2e-5
+        assert rel_err(a, b) <= 5e-5

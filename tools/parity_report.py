@@ -18,6 +18,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+TRUTH_FEATURES = False      # --truth-features: feed the hot path the float64 oracle's feature maps (isolates the encoder)
+
 CONFIGS = {
     "small": dict(B=2, H=136, W=240, max_disp=192, K=4, L=(2, 3, 2), index=2),
     "half": dict(B=1, H=270, W=480, max_disp=192, K=4, L=(5, 5, 5), index=2),
@@ -39,7 +41,7 @@ def report(cfgname, pairs):
     for i in range(pairs):
         t0 = time.time()
         img1, img2 = synthetic_pair(c["B"], c["H"], c["W"], c["max_disp"], index=c["index"] + i)
-        m, o, t = parity_metrics(model, sd, c["max_disp"], c["K"], c["L"], img1, img2)
+        m, o, t = parity_metrics(model, sd, c["max_disp"], c["K"], c["L"], img1, img2, truth_features=TRUTH_FEATURES)
         m["index"] = c["index"] + i
         m["seconds"] = round(time.time() - t0, 1)
         if i == 0 and "truth" in c:
@@ -59,7 +61,9 @@ if __name__ == "__main__":
     ap.add_argument("--config", nargs="+", default=["small"])
     ap.add_argument("--pairs", type=int, default=1, help="consecutive synthetic pair indices to report per config")
     ap.add_argument("--tag", default="default")
+    ap.add_argument("--truth-features", action="store_true")
     args = ap.parse_args()
+    TRUTH_FEATURES = args.truth_features
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     for name in args.config:
         r = report(name, args.pairs)

@@ -1,16 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- stereo pairs/s of the NMRF-Stereo inference path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config c1|c1b|c2|c3|c4]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...     (one rank per GPU)
 
-Workload (config.workload): BASELINE.json configs[1] -- SceneFlow 540x960 (padded 544x960), D_max=192 (D=24),
-K=4 proposals, 8/8/8 layers ("8 iters"), batch 1 per GPU, fp32, synthetic images and
-seeded random-init weights (no datasets/checkpoints offline).  A step = one forward over one batch.
+Workload (config.workload), default c1 = BASELINE.json configs[1] -- SceneFlow 540x960 (padded 544x960), D_max=192 (D=24),
+K=4 proposals, 8/8/8 layers ("8 iters"), batch 1 per GPU, fp32, synthetic images and seeded random-init
+weights (no datasets/checkpoints offline).  A step = one forward over one batch.  --config selects the other BASELINE
+configurations: c1b = c1 at the checkpoint-compatible depth 5/5/5; c2 = KITTI 375x1248, batch 8; c3 =
+SceneFlow batch 8 per rank (run with --gpus 4: batch 32 over 4 GPUs); c4 = Swin-T encoder (the reference's own module from
+baseline/_ref, with nmrf_b200.msda as its deformable-attention op), 1000x1500, D_max=256, one pair per rank (--gpus 8).
 
   value  : pairs/s of the hot path (every libnmrf_b200 kernel from the cost volume to the disparity map, one CUDA
            graph) over feature maps resident in HBM; CUDA-event time per step, L2 flushed between steps, max over
-           ranks.  `full_forward` reports the same with the torch feature extractor included.
+           ranks.  `full_forward` reports the same with the feature extractor included.
   e2e    : the whole forward through the public streaming API (`GraphedNMRF.stream`) with pinned HOST images: H2D of both
            images and D2H of the disparity map of every step inside the timed region, overlapped with the neighbouring
            steps' compute (the number to hold against `--impl reference`).
@@ -34,8 +37,20 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-WORKLOAD = dict(name="sceneflow_540x960_D192_K4_L8", B=1, H=540, W=960, max_disp=192, K=4, L=(8, 8, 8))
-METRIC = "stereo pairs/sec at 960x540 D192 K4 8-iter"
+WORKLOADS = {
+    "c1": dict(name="sceneflow_540x960_D192_K4_L8", B=1, H=540, W=960, max_disp=192, K=4, L=(8, 8, 8),
+               metric="stereo pairs/sec at 960x540 D192 K4 8-iter"),
+    "c1b": dict(name="sceneflow_540x960_D192_K4_L5", B=1, H=540, W=960, max_disp=192, K=4, L=(5, 5, 5),
+                metric="stereo pairs/sec at 960x540 D192 K4 5/5/5 layers (checkpoint-compatible depth)"),
+    "c2": dict(name="kitti_375x1248_D192_K4_L8_batch8", B=8, H=375, W=1248, max_disp=192, K=4, L=(8, 8, 8),
+               metric="stereo pairs/sec at KITTI 1248x375 D192 K4 8-iter, batch 8"),
+    "c3": dict(name="sceneflow_540x960_D192_K4_L8_batch8_per_gpu", B=8, H=540, W=960, max_disp=192, K=4, L=(8, 8, 8),
+               metric="stereo pairs/sec at 960x540 D192 K4 8-iter, batch 8 per GPU (batch 32 on 4 GPUs)"),
+    "c4": dict(name="swint_1000x1500_D256_K4_L8", B=1, H=1000, W=1500, max_disp=256, K=4, L=(8, 8, 8), swin=True,
+               metric="stereo pairs/sec at 1500x1000 D256 K4 8-iter, Swin-T encoder, 1 pair per GPU"),
+}
+WORKLOAD = WORKLOADS["c1"]
+METRIC = WORKLOAD["metric"]
 N_PAIRS = 4                 # distinct synthetic pairs rotated through the timed steps
 FLUSH_BYTES = 256 << 20     # > 126 MB L2
 
@@ -94,6 +109,14 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def reference_tree_on_path():
+    """the staged reference (baseline/_ref, written by baseline/stage_reference.py) for the Swin-T encoder of config c4"""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if os.path.isdir(os.path.join(ref, "nmrf")) and ref not in sys.path:
+        sys.path.insert(0, ref)
+    return os.path.isdir(os.path.join(ref, "nmrf"))
+
+
 def build_model(device):
     import nmrf_b200
     from nmrf_b200.synthetic import synthetic_state_dict
@@ -101,6 +124,10 @@ def build_model(device):
     cfg = nmrf_b200.get_cfg()
     cfg.DPN.MAX_DISP, cfg.DPN.NUM_PROPOSALS = w["max_disp"], w["K"]
     cfg.NMP.NUM_PROP_LAYERS, cfg.NMP.NUM_INFER_LAYERS, cfg.NMP.NUM_REFINE_LAYERS = w["L"]
+    if w.get("swin"):                                  # configs/sceneflow_swint.yaml:3-7
+        cfg.BACKBONE.MODEL_TYPE, cfg.BACKBONE.OUT_CHANNELS, cfg.BACKBONE.DROP_PATH, cfg.DATASETS.DIVIS_BY = "swin", 128, 0.0, 32
+        cfg.BACKBONE.COMPAT = False
+        reference_tree_on_path()
     model = nmrf_b200.build_model(cfg).eval()
     sd = synthetic_state_dict(model.state_dict(), 0, "reference")
     model.load_state_dict(sd)
@@ -197,11 +224,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c1", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global WORKLOAD, METRIC
+    WORKLOAD = WORKLOADS[args.config]
+    METRIC = WORKLOAD["metric"]
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if WORKLOAD.get("swin"):
+        import importlib.util
+        missing = None if reference_tree_on_path() else "baseline/_ref (the staged reference tree) is absent"
+        if missing is None and importlib.util.find_spec("timm") is None:
+            missing = "the reference's Swin-T encoder needs timm, which is not installed in this image"
+        if missing:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "config": {"workload": WORKLOAD["name"]}, "unavailable": missing}))
+            return
 
     from nmrf_b200 import _lib
     from nmrf_b200.runner import GraphedNMRF
@@ -282,11 +322,11 @@ def main():
     dom = max(agg, key=lambda k: agg[k]["ms"])
     d = agg[dom]
     ai = d["flops"] / max(d["bytes"], 1.0)
-    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r1_ncu_traffic.json)
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/r2_ncu_traffic.json; c1 only)
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")))
-        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch") if args.config == "c1" else None
     except Exception:
         pass
     # the path's arithmetic is 3xTF32 (the 1e-3 EPE bar): its ceiling is 1/6 of the dense bf16 peak.  A kernel
@@ -330,8 +370,8 @@ def main():
                        "l2": "flushed between timed steps (256 MiB memset)", "cuda_graph": True,
                        "gemm": "tcgen05 3xTF32" if plan.launches.tensor_cores else "fp32 FMA"},
             "full_forward": {"value": pairs_total / t_dev_max, "unit": "pairs/s", "ms_per_step": 1e3 * t_dev_max / steps,
-                             "includes": "torch feature extractor + conv heads (cuDNN, 3xTF32-exact) + hot path, one CUDA graph, "
-                                         "device-resident images"},
+                             "includes": "feature extractor + conv heads (nmrf_conv2d on tcgen05, own glue kernels) + hot path, one CUDA "
+                                         "graph, device-resident images"},
             "e2e": {"value": pairs_total / t_e2e_max, "unit": "pairs/s", "h2d_bytes_per_step": img_bytes,
                     "d2h_bytes_per_step": B * H * W * 4},
             "gpu_launches": launches_per_step * steps,

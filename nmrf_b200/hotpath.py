@@ -319,12 +319,15 @@ class HotPathPlan:
         sw = SeedWeights(*[ptr(pw.seed[k]) for k in ("w0", "b0", "w1", "b1", "w2", "b2")])
         L_.keep(sw)
         L_.add(lib.nmrf_cost_volume_topk, "cost_volume_topk", ptr(self.f1_8), ptr(self.f2_8), B, h8, w8, C, G, D, K,
-               c.eps, ctypes.byref(sw), ptr(self.cost_volume), ptr(self.prob), ptr(self.seeds))
+               c.eps, ctypes.byref(sw), ptr(self.cost_volume), ptr(self.prob), ptr(self.seeds),
+               # algorithmic bytes (SURVEY.md §8(d), S1 + S2 fused): both feature maps in, cost volume + prob + int64 seeds out
+               bytes=4.0 * (2 * P8 * C + P8 * G * D + P8 * D) + 8.0 * P8 * K,
+               flops=2.0 * P8 * D * C + 2.0 * P8 * D * 5 * (G * 8 + 8 * 16 + 16))
         # A3+A4 -------------------------------------------------------------------------------------
         ext = int(self.labels_lo is not None)
         optr = lambda t: None if t is None else t.data_ptr()
         L_.add(lib.nmrf_prop_gather, "prop_gather", ptr(self.cost_volume), ptr(self.seeds), P8, G, D, K, 3.14 / 64, ext,
-               ptr(self.cost48), 48, ptr(self.enc))
+               ptr(self.cost48), 48, ptr(self.enc), bytes=4.0 * (P8 * G * D + T8 * (48 + 32)) + 8.0 * T8)
         L_.gemm("cost_encoder.0", self.cost48, pw.ce0_w, self.h1, T8, 128, bias=pw.ce0_b, act=ACT_GELU)
         L_.gemm("cost_encoder.2", self.h1, pw.ce2_w, self.h2, T8, 128, bias=pw.ce2_b)
         L_.gemm("propagation.proj", self.h2, pw.pproj_w, self.x, T8, 128, E=self.enc, Ke=32)
@@ -333,15 +336,17 @@ class HotPathPlan:
         for i, w in enumerate(pw.prop_layers):
             t = f"prop{i}"
             L_.gemm(t + ".qkv", self.x, w["qkv_w"], self.qkv, T8, 384, E=ctx, Ke=64, ediv=K, ln=w["n1"], bias=w["qkv_b"])
+            # stripe attention (A6): 2 heads x (q.k^T + p.v) x 32 dims over full-height and full-width stripes; qkv in, att out
             L_.add(lib.nmrf_stripe_attention, t + ".stripe", ptr(self.qkv), B, h8, w8, K, ptr(w["gv0"]), ptr(w["gv1"]),
-                   ptr(self.att))
+                   ptr(self.att), bytes=4.0 * T8 * (384 + 128),
+                   flops=2.0 * B * (w8 * 2 * (h8 * K) ** 2 * 32 * 2 + h8 * 2 * (w8 * K) ** 2 * 32 * 2))
             self._block_tail(L_, T8, w, t)
         # A7 ----------------------------------------------------------------------------------------
         (w0, b0), (w1, b1), (w2, b2) = pw.prop_head
         L_.gemm("prop_head.0", self.x, w0, self.h1, T8, 128, ln=pw.prop_norm, bias=b0, act=ACT_RELU)
         L_.gemm("prop_head.1", self.h1, w1, self.h2, T8, 128, bias=b1, act=ACT_RELU)
         L_.add(lib.nmrf_prop_head_tail, "prop_head.2", ptr(self.h2), ptr(w2), ptr(b2), ptr(self.seeds), T8, ptr(self.labels),
-               optr(self.labels_lo))
+               optr(self.labels_lo), bytes=4.0 * T8 * 128 + 8.0 * T8 + 8.0 * T8)
 
         # A8-A12: inference @1/8 --------------------------------------------------------------------
         self._stack(L_, pw.stacks["inference"], "inference", self.labels, self.labels_lo, self.cc8, self.gw8, h8, w8, K,
@@ -355,7 +360,8 @@ class HotPathPlan:
         # 0.25 * score (NMRF.py:220) does not change the argmax: the exact power-of-two scale is dropped
         L_.gemm("infer_score_head", self.x, pw.score_head[0], self.score, T8p, 64, ln=nrm, bias=pw.score_head[1])
         L_.add(lib.nmrf_select_median, "select_median", ptr(self.delta), ptr(self.score), ptr(self.labels), optr(self.labels_lo),
-               B, h8, w8, K, g["Hp8"], g["Wp8"], g["top8"], g["left8"], ptr(self.disp_curr), optr(self.disp_curr_lo))
+               B, h8, w8, K, g["Hp8"], g["Wp8"], g["top8"], g["left8"], ptr(self.disp_curr), optr(self.disp_curr_lo),
+               bytes=4.0 * (2 * T8 * 64 + 2 * T8 + 2 * g["P4"]))
 
         # A13: refinement @1/4 ----------------------------------------------------------------------
         h4, w4 = g["h4"], g["w4"]
@@ -369,7 +375,8 @@ class HotPathPlan:
         delta16 = self.delta.view(-1)[:T4p * 16].view(T4p, 16)      # dense [T4p,16] as nmrf_refine_tail expects
         L_.gemm("refine_head.2", self.h2, w2, delta16, T4p, 16, bias=b2)
         L_.add(lib.nmrf_refine_tail, "refine_tail", ptr(delta16), ptr(self.disp_curr), optr(self.disp_curr_lo), B, h4, w4, g["Hp4"], g["Wp4"],
-               g["top4"], g["left4"], self.H, self.W, ptr(self.disp_pred), ptr(self.disp))
+               g["top4"], g["left4"], self.H, self.W, ptr(self.disp_pred), ptr(self.disp),
+               bytes=4.0 * (g["P4"] * 16 + 2 * g["P4"] + 2 * B * 16 * h4 * w4))
 
     def _stack(self, L_, S, name, labels, labels_lo, cc, gw, h, w, K, Hp, Wp, top, left, ws, normalizer, with_self):
         B = self.B
@@ -377,22 +384,28 @@ class HotPathPlan:
         Tp = B * Hp * Wp * K
         L_.add(lib.nmrf_warp_corr_embed, name + ".embed", ptr(cc[0]), ptr(cc[1]), ptr(gw[0]), ptr(gw[1]), ptr(labels),
                None if labels_lo is None else ptr(labels_lo), B, h, w, K, Hp, Wp, top, left, normalizer, ptr(self.feat),
-               ptr(self.enc))
+               ptr(self.enc),
+               # S6 / S9: the four feature maps (64 + 64 + 256 + 256 channels) once, labels, feat [Tp,160] + enc [Tp,32] out
+               bytes=4.0 * (640 * B * h * w + 2 * B * h * w * K + Tp * 192))
         L_.gemm(name + ".ffn.fc1", self.feat, S["ffn1_w"], self.h1, Tp, 128, bias=S["ffn1_b"], act=ACT_GELU)
         L_.gemm(name + ".ffn.fc2", self.h1, S["ffn2_w"], self.x, Tp, 128, bias=S["ffn2_b"])
         if Hp != h or Wp != w:
-            L_.add(lib.nmrf_zero_pad_rows, name + ".zero_pad", ptr(self.x), B, h, w, K, Hp, Wp, top, left)
+            L_.add(lib.nmrf_zero_pad_rows, name + ".zero_pad", ptr(self.x), B, h, w, K, Hp, Wp, top, left,
+                   bytes=4.0 * 128 * (Tp - B * h * w * K))
         for i, wt in enumerate(S["layers"]):
             t = f"{name}{i}"
             shift = 0 if i % 2 == 0 else ws // 2                     # NMRF.py:72,96
             if with_self:
                 L_.gemm(t + ".self.qkv", self.x, wt["s_qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["s_n1"],
                         bias=wt["s_qkv_b"])
-                L_.add(lib.nmrf_proposal_attention, t + ".self.attn", ptr(self.qkv), Tp // K, K, ptr(self.att))
+                L_.add(lib.nmrf_proposal_attention, t + ".self.attn", ptr(self.qkv), Tp // K, K, ptr(self.att),
+                       bytes=4.0 * Tp * (384 + 128), flops=2.0 * (Tp // K) * 4 * K * K * 32 * 2)
                 L_.gemm(t + ".self.proj", self.att, wt["s_proj_w"], self.x, Tp, 128, bias=wt["s_proj_b"], R=self.x)
             L_.gemm(t + ".qkv", self.x, wt["qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["n1"], bias=wt["qkv_b"])
+            # window attention (A11): 4 heads x 5 contractions of (ws^2 K)^2 x 32 per window (q.k, q.Rk, k.Rq, A.v, A.Rv; H4)
             L_.add(lib.nmrf_window_attention, t + ".window", ptr(self.qkv), ptr(wt["table"]), B, Hp, Wp, K, ws, shift,
-                   1 if with_self else 0, ptr(self.att))
+                   1 if with_self else 0, ptr(self.att), bytes=4.0 * Tp * (384 + 128),
+                   flops=2.0 * (B * (Hp // ws) * (Wp // ws)) * 4 * (ws * ws * K) ** 2 * 32 * 5)
             self._block_tail(L_, Tp, wt, t)
 
     # -------------------------------------------------------------------------------------------

@@ -234,10 +234,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if WORKLOAD.get("swin"):
-        import importlib.util
-        missing = None if reference_tree_on_path() else "baseline/_ref (the staged reference tree) is absent"
-        if missing is None and importlib.util.find_spec("timm") is None:
-            missing = "the reference's Swin-T encoder needs timm, which is not installed in this image"
+        missing = None if reference_tree_on_path() else "baseline/_ref (the staged reference tree: baseline/stage_reference.py) is absent"
         if missing:
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "config": {"workload": WORKLOAD["name"]}, "unavailable": missing}))

@@ -61,6 +61,8 @@ typedef struct {
   const float* X; int ldx; int Kx;
   const float* E; int lde; int Ke; int ediv;   /* E may be NULL (Ke = 0) */
   const float* ln_gamma; const float* ln_beta; /* both NULL = no LayerNorm; else Kx must be 128 */
+  const float* ln_stats;                       /* optional [rows, 2] = (mean, 1 / sqrt(var + 1e-5)) of every row of X, as written by
+                                                  nmrf_mlp_chain (out_stats) or nmrf_row_stats; NULL: the kernel computes them */
   const float* W; int ldw;
   const float* bias;                           /* [N] or NULL */
   const float* R; int ldr;                     /* residual or NULL; may alias Y */
@@ -76,6 +78,8 @@ typedef struct {
   const float* Wt_lo;
 } nmrf_gemm_args;
 int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream);
+/* LayerNorm statistics of every row of X [rows, 128] (two-pass, eps 1e-5): stats [rows, 2] = (mean, rstd) */
+int nmrf_row_stats(const float* X, int ldx, int rows, float* stats, void* stream);
 /* w [N,K] row-major (device) -> hi/lo tile images, K zero-padded to a multiple of 32, N to a multiple of 128:
  * hi_tiles / lo_tiles must hold ceil(N/128)*ceil(K/32)*4096 floats each. */
 int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float* lo_tiles, void* stream);
@@ -104,6 +108,7 @@ typedef struct {
   const float* bias_out;                       /* [128] fc2 bias */
   float* Y; int ldy;
   int rows;
+  float* out_stats;                            /* optional [rows, 2]: (mean, rstd) of every OUTPUT row (the next block's LayerNorm) */
   int e_identity;                              /* 1: E [rows,128] is the residual, added in fp32 registers (not part of the weight stream) */
 } nmrf_mlp_args;
 int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream);

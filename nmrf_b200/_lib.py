@@ -19,6 +19,7 @@ class GemmArgs(Structure):
         ("X", c_void_p), ("ldx", c_int), ("Kx", c_int),
         ("E", c_void_p), ("lde", c_int), ("Ke", c_int), ("ediv", c_int),
         ("ln_gamma", c_void_p), ("ln_beta", c_void_p),
+        ("ln_stats", c_void_p),
         ("W", c_void_p), ("ldw", c_int),
         ("bias", c_void_p),
         ("R", c_void_p), ("ldr", c_int),
@@ -40,7 +41,9 @@ class MlpArgs(Structure):
         ("b1", c_void_p),
         ("bias_out", c_void_p),
         ("Y", c_void_p), ("ldy", c_int),
-        ("rows", c_int), ("e_identity", c_int),
+        ("rows", c_int),
+        ("out_stats", c_void_p),
+        ("e_identity", c_int),
     ]
 
 
@@ -68,6 +71,7 @@ SIGNATURES = {
     "nmrf_token_gemm": [POINTER(GemmArgs), _P],
     "nmrf_mlp_chain": [POINTER(MlpArgs), _P],
     "nmrf_conv2d": [POINTER(ConvArgs), _P],
+    "nmrf_row_stats": [_P, _I, _I, _P, _P],
     "nmrf_split_tf32": [_P, _P, _P, c_int64, _P],
     "nmrf_instnorm_stats": [_P, _I, _I, _I, _P, _P],
     "nmrf_instnorm_apply": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P],

@@ -75,14 +75,15 @@ def create_backbone(cfg):
             raise ValueError(f"Invalid backbone normalization type: {cfg.BACKBONE.NORM_FN}")
         return Backbone(cfg.BACKBONE.OUT_CHANNELS, norm_layer)
     if model_type == "swin":
-        from . import msda
-        msda.install_as_reference_extension()
+        from . import msda, ref_compat
+        msda.install_as_reference_extension()                      # the encoder's one native op (boundary B2)
+        ref_compat.install_missing()                               # timm / yacs / omegaconf / imageio stand-ins where absent
         try:
             from nmrf.models.backbone import SwinAdaptor          # the reference's module, unmodified
-        except Exception as e:                                     # not on sys.path, or its own dependencies are missing
+        except Exception as e:                                     # the reference tree is not on sys.path
             raise NotImplementedError(
                 "BACKBONE.MODEL_TYPE='swin' uses the reference's SwinAdaptor (nmrf/models/backbone.py:101-158): put the reference "
-                f"tree on sys.path (and its dependencies, e.g. timm) -- import failed with: {e!r}") from e
+                f"tree on sys.path (baseline/stage_reference.py stages it under baseline/_ref) -- import failed with: {e!r}") from e
         backbone = SwinAdaptor(out_channels=cfg.BACKBONE.OUT_CHANNELS, drop_path_rate=cfg.BACKBONE.DROP_PATH)
         if cfg.BACKBONE.WEIGHT_URL:
             import torch

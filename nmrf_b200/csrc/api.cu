@@ -40,6 +40,7 @@ int check_launch(const char* what) {
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
 int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream);
 int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream);
+int row_stats(const float* X, int ldx, int rows, float* stats, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
 int mlp_set_trace(long long* dev_ptr);
@@ -74,7 +75,7 @@ int ms_deform_attn_forward(const float*, const int64_t*, const int64_t*, const f
 
 using namespace nmrf;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
-static_assert(sizeof(nmrf_gemm_args) == 136 && sizeof(nmrf_mlp_args) == 104, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
+static_assert(sizeof(nmrf_gemm_args) == 144 && sizeof(nmrf_mlp_args) == 112, "ctypes mirrors in nmrf_b200/_lib.py assume these layouts");
 
 // NMRF_B200_ATTN=simt selects the fp32-FMA attention kernels (default: tcgen05 3xTF32)
 static std::atomic<int> g_attn_tc{-1};
@@ -125,6 +126,7 @@ int nmrf_mlp_chain(const nmrf_mlp_args* a, void* stream) {
   if (a->rows == 0) return NMRF_OK;
   return mlp_chain(*a, ST(stream));
 }
+int nmrf_row_stats(const float* X, int ldx, int rows, float* stats, void* stream) { return row_stats(X, ldx, rows, stats, ST(stream)); }
 int nmrf_conv2d(const nmrf_conv_args* c, void* stream) {
   NMRF_REQUIRE(c != nullptr, "conv2d: null argument struct");
   return conv2d_tc6(*c, ST(stream));

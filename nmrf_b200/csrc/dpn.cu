@@ -6,40 +6,90 @@
 namespace nmrf {
 namespace {
 
-constexpr int TX = 32;          // pixels of one image row per CTA
+constexpr int TX = 16;          // pixels of one image row per CTA
 constexpr int CV_THREADS = 256;
+constexpr int CV_WARPS = CV_THREADS / 32;
 
-// One CTA = TX consecutive pixels of one 1/8-res row.  Both feature rows are staged in shared
-// memory once (f2 with a D-1 halo to the left), so HBM sees each feature byte ~once; the cost
-// slab [TX,G,D], the three tiny conv1d layers, softmax, NMS and top-K never leave the SM.
-//   smem: f1 [TX][C+4], f2 [TX+D-1][C+4]  (dead after A1, re-used for h1 [TX][8][D+4], h2 [TX][16][D+4]),
-//         cv [TX][G][D+4], logits [TX][D], conv weights
+__device__ __forceinline__ uint32_t cv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// conv1d (kernel 5, padding 2) over D for one (pixel, output channel): `in` = the pixel's CI input rows in shared memory (row
+// stride DP floats, value d at position d + 2, zeros around it), 5 CI weights in registers.  Four outputs per step from two
+// aligned 16-byte loads per input row (20 FMAs per 2 loads; the round-1 kernel read one weight from shared memory per FMA).
+template <int CI>
+__device__ __forceinline__ void conv5_row(const float* __restrict__ in, int DP, int D, const float (&w)[CI][5], float bias, bool relu,
+                                          float* __restrict__ out /* row, position d + 2 */) {
+  for (int d0 = 0; d0 < D; d0 += 4) {
+    float acc[4] = {bias, bias, bias, bias};
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) {
+      const float4 a = *reinterpret_cast<const float4*>(in + ci * DP + d0);
+      const float4 b = *reinterpret_cast<const float4*>(in + ci * DP + d0 + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};          // positions d0 .. d0+7 = taps d0-2 .. d0+5
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[ci][k], v[j + k], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (d0 + j < D) out[2 + d0 + j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
+  }
+}
+
+// One CTA = TX consecutive pixels of one 1/8-res row (B*h*ceil(w/TX) CTAs: 544 at 68x120, 3 760 for a KITTI batch of 8; three
+// CTAs share an SM).  HBM sees every byte about once and nothing between the two feature maps and the outputs leaves the SM:
+//   stage   the f1 tile (TX pixels) and the f2 tile with its D-1 halo are each ONE contiguous run of an NHWC row: two TMA
+//           bulk copies (cp.async.bulk -> mbarrier), no per-thread loads;
+//   A1      group-wise correlation: warp = pixel, lane = C/32 channels; f1 stays in registers over d, the G group sums come
+//           from xor-shuffles; the [TX,G,D] slab is assembled in shared memory and leaves as ONE contiguous run of
+//           cost_volume (16-byte coalesced stores), not as scattered 4-byte stores;
+//   A2      conv1d G->8->16->1: thread = (pixel, output channel), its 5 CI weights in registers, four d per step (conv5_row);
+//           softmax, 1-D NMS and top-K: WARP per pixel, lane = d, shuffles (the round-1 kernel ran them on 32 threads of
+//           the CTA, serially over D).
+//   smem: f1 [TX][C], f2 [TX+D-1][C]  (dead after A1, re-used for h1 [TX][8][DP], h2 [TX][16][DP]), cv [TX][G][DP] (conv
+//         input, zero halos), logits [TX][D], conv weights: 70 KB at C = 256, D = 24
 __global__ void __launch_bounds__(CV_THREADS)
 cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
                         int h, int w, int C, int G, int D, int K, float eps,
                         nmrf_seed_weights wt,
                         float* __restrict__ cost_volume, float* __restrict__ prob_out,
                         int64_t* __restrict__ seeds) {
-  extern __shared__ __align__(16) float smem[];
-  const int CS = C + 4;                      // padded channel stride (bank spread for float4 rows)
-  const int DP = D + 4;                      // conv halo of 2 on both sides
-  const int featN = (2 * TX + D - 1) * CS, hidN = TX * 24 * DP;
-  float* s_f1 = smem;                        // TX*CS
-  float* s_f2 = s_f1 + TX * CS;              // (TX+D-1)*CS
+  extern __shared__ __align__(128) float smem[];
+  const int DP = (D + 4 + 3 + 3) & ~3;       // row stride: value d at d + 2, zeros elsewhere; loads reach d0 + 7 <= roundup(D,4) + 3
+  const int featN = (2 * TX + D - 1) * C, hidN = TX * 24 * DP;
+  float* s_f1 = smem;                        // TX*C
+  float* s_f2 = s_f1 + TX * C;               // (TX+D-1)*C
   float* s_h1 = smem;                        // TX*8*DP   (aliases the feature staging)
   float* s_h2 = s_h1 + TX * 8 * DP;          // TX*16*DP
   float* s_cv = smem + (featN > hidN ? featN : hidN);   // TX*G*DP
-  float* s_lg = s_cv + TX * G * DP;          // TX*D logits -> prob
-  float* s_w = s_lg + TX * D;                // conv weights: 8*G*5 + 8 + 16*8*5 + 16 + 16*5 + 1
+  float* s_lg = s_cv + TX * G * DP;          // TX*D logits
+  float* s_w = s_lg + ((TX * D + 3) & ~3);   // conv weights: 8*G*5 + 8 + 16*8*5 + 16 + 16*5 + 1
+  __shared__ __align__(8) unsigned long long bar;
 
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_x = (w + TX - 1) / TX;
   const int tile = blockIdx.x % tiles_x;
   const int by = blockIdx.x / tiles_x;       // b*h + y
   const int x0 = tile * TX;
+  const int ntx = min(TX, w - x0);           // pixels of this tile inside the row
   const size_t row_base = (size_t)by * w;    // pixel index of (b,y,0)
 
-  // ---- stage weights and features -----------------------------------------------------------
+  // ---- stage: TMA bulk copies of the two feature tiles (one elected thread), weights by everybody meanwhile ---------------
+  const uint32_t bar_a = cv_smem_u32(&bar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int xs = max(x0 - (D - 1), 0);                        // first f2 pixel that exists
+    const uint32_t bytes1 = (uint32_t)ntx * C * 4, bytes2 = (uint32_t)(x0 + ntx - xs) * C * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes1 + bytes2) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cv_smem_u32(s_f1)), "l"(f1 + (row_base + x0) * C), "r"(bytes1), "r"(bar_a) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cv_smem_u32(s_f2 + (size_t)(xs - (x0 - (D - 1))) * C)), "l"(f2 + (row_base + xs) * C), "r"(bytes2), "r"(bar_a) : "memory");
+  }
   const int nw0 = 8 * G * 5, nw1 = 16 * 8 * 5, nw2 = 16 * 5;
   float* sw0 = s_w; float* sb0 = sw0 + nw0; float* sw1 = sb0 + 8; float* sb1 = sw1 + nw1;
   float* sw2 = sb1 + 16; float* sb2 = sw2 + nw2;
@@ -49,135 +99,197 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
   if (tid < 8) sb0[tid] = wt.b0[tid];
   if (tid < 16) sb1[tid] = wt.b1[tid];
   if (tid == 0) sb2[0] = wt.b2[0];
-
-  const int c4 = C / 4;
-  for (int i = tid; i < TX * c4; i += CV_THREADS) {
-    const int px = i / c4, c = (i % c4) * 4;
-    const int x = x0 + px;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x < w) v = __ldg(reinterpret_cast<const float4*>(f1 + (row_base + x) * C + c));
-    *reinterpret_cast<float4*>(s_f1 + px * CS + c) = v;
+  for (int i = tid; i < TX * G * DP; i += CV_THREADS) s_cv[i] = 0.f;   // conv halos (and the columns of pixels past the row end)
+  {                                                                   // wait for the tiles (every thread observes the barrier)
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar_a) : "memory");
   }
-  for (int i = tid; i < (TX + D - 1) * c4; i += CV_THREADS) {
-    const int px = i / c4, c = (i % c4) * 4;
-    const int x = x0 - (D - 1) + px;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x >= 0 && x < w) v = __ldg(reinterpret_cast<const float4*>(f2 + (row_base + x) * C + c));
-    *reinterpret_cast<float4*>(s_f2 + px * CS + c) = v;
-  }
-  for (int i = tid; i < TX * G * DP; i += CV_THREADS) s_cv[i] = 0.f;   // conv halo
   __syncthreads();
 
-  // ---- A1: group-wise correlation.  One warp per (pixel, d): lanes span channels, a group is
-  //      C/G consecutive channels = (32/G) lanes when C/32 channels sit in each lane.
+  // ---- A1: group-wise correlation.  warp = pixel (TX / 8 pixels per warp), lane = C/32 consecutive channels; a group is
+  //      32/G consecutive lanes.  Pixels left of the image (x < d) read whatever the halo holds: their value is SELECTED to 0.
   {
-    const int warp = tid >> 5, lane = tid & 31;
-    const int cpl = C / 32;                       // channels per lane (8 for C=256, 4 for C=128)
-    const int lanes_per_group = 32 / G;
+    const int cpl = C / 32;                       // channels per lane: 4 (C=128), 8 (C=256), 16 (C=512)
+    const int lpg = 32 / G;                       // lanes per group
     const float inv = 1.f / (float)(C / G);
-    for (int item = warp; item < TX * D; item += CV_THREADS / 32) {
-      const int px = item / D, d = item % D;
+    const int g = lane / lpg;
+    for (int px = warp; px < ntx; px += CV_WARPS) {
       const int x = x0 + px;
-      const float* a = s_f1 + px * CS + lane * cpl;
-      const float* b = s_f2 + (px + (D - 1) - d) * CS + lane * cpl;
-      float s = 0.f;
-      for (int c = 0; c < cpl; c += 4) {
-        const float4 va = *reinterpret_cast<const float4*>(a + c);
-        const float4 vb = *reinterpret_cast<const float4*>(b + c);
-        s = fmaf(va.x, vb.x, s); s = fmaf(va.y, vb.y, s);
-        s = fmaf(va.z, vb.z, s); s = fmaf(va.w, vb.w, s);
-      }
-      for (int o = lanes_per_group >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if ((lane % lanes_per_group) == 0 && x < w) {
-        const int g = lane / lanes_per_group;
-        const float v = (x >= d) ? s * inv : 0.f;
-        s_cv[(px * G + g) * DP + 2 + d] = v;
-        cost_volume[((row_base + x) * G + g) * D + d] = v;
+      float a[16];
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        if (c < cpl) *reinterpret_cast<float4*>(a + c) = *reinterpret_cast<const float4*>(s_f1 + px * C + lane * cpl + c);
+      for (int d0 = 0; d0 < D; d0 += 4) {         // four disparities in flight
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int d = min(d0 + j, D - 1);
+          const float* b = s_f2 + (size_t)(px + (D - 1) - d) * C + lane * cpl;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4)
+            if (c < cpl) {
+              const float4 vb = *reinterpret_cast<const float4*>(b + c);
+              s[j] = fmaf(a[c], vb.x, s[j]); s[j] = fmaf(a[c + 1], vb.y, s[j]);
+              s[j] = fmaf(a[c + 2], vb.z, s[j]); s[j] = fmaf(a[c + 3], vb.w, s[j]);
+            }
+        }
+        for (int o = lpg >> 1; o > 0; o >>= 1) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        }
+        if ((lane % lpg) == 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = d0 + j;
+            if (d < D) {
+              const float v = (x >= d) ? s[j] * inv : 0.f;
+              s_cv[(px * G + g) * DP + 2 + d] = v;
+            }
+          }
+        }
       }
     }
   }
   __syncthreads();
-  for (int i = tid; i < TX * 24 * DP; i += CV_THREADS) s_h1[i] = 0.f;   // features are dead: zero h1|h2 (+halos)
+  // the tile's [ntx, G, D] slab is one contiguous run of cost_volume: coalesced 16-byte stores, consecutive threads ->
+  // consecutive addresses (a (pixel, group) row of D floats sits at offset 2 of its shared-memory row: two 8-byte reads)
+  {
+    float* dst = cost_volume + (row_base + x0) * G * D;
+    if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+      const int q4 = D >> 2, n4 = ntx * G * q4;
+      for (int i = tid; i < n4; i += CV_THREADS) {
+        const int r = i / q4, q = i - r * q4;
+        const float2 lo = *reinterpret_cast<const float2*>(s_cv + r * DP + 2 + q * 4);
+        const float2 hi = *reinterpret_cast<const float2*>(s_cv + r * DP + 4 + q * 4);
+        reinterpret_cast<float4*>(dst)[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      }
+    } else {
+      for (int i = tid; i < ntx * G * D; i += CV_THREADS) dst[i] = s_cv[(i / D) * DP + 2 + i % D];
+    }
+  }
+  // features are dead: zero the halos of h1 | h2 (value d lives at d + 2; everything else in a row must read as zero padding)
+  for (int r = tid; r < TX * 24; r += CV_THREADS) {
+    float* row = s_h1 + r * DP;
+    row[0] = 0.f; row[1] = 0.f;
+    for (int i = D + 2; i < DP; ++i) row[i] = 0.f;
+  }
   __syncthreads();
 
-  // ---- A2: conv1d 4->8 (k5) + ReLU ------------------------------------------------------------
-  for (int item = tid; item < TX * D; item += CV_THREADS) {
-    const int px = item / D, d = item % D;
-    float o[8];
+  // ---- A2: conv1d G->8 (k5) + ReLU: thread = (pixel, output channel) ---------------------------------------------------
+  if (tid < TX * 8) {
+    const int px = tid >> 3, co = tid & 7;
+    float wr[8][5];
 #pragma unroll
-    for (int co = 0; co < 8; ++co) o[co] = sb0[co];
-    for (int ci = 0; ci < G; ++ci) {
-      const float* src = s_cv + (px * G + ci) * DP + d;   // taps d-2..d+2 live at +0..+4
-      float t[5];
+    for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
-      for (int k = 0; k < 5; ++k) t[k] = src[k];
-#pragma unroll
-      for (int co = 0; co < 8; ++co)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) o[co] = fmaf(sw0[(co * G + ci) * 5 + k], t[k], o[co]);
+      for (int k = 0; k < 5; ++k) wr[ci][k] = ci < G ? sw0[(co * G + ci) * 5 + k] : 0.f;
+    const float* in = s_cv + px * G * DP;
+    float* out = s_h1 + (px * 8 + co) * DP;
+    switch (G) {                                   // the input-channel count is a loop bound of fully unrolled code
+      case 1: conv5_row<1>(in, DP, D, reinterpret_cast<const float(&)[1][5]>(wr), sb0[co], true, out); break;
+      case 2: conv5_row<2>(in, DP, D, reinterpret_cast<const float(&)[2][5]>(wr), sb0[co], true, out); break;
+      case 4: conv5_row<4>(in, DP, D, reinterpret_cast<const float(&)[4][5]>(wr), sb0[co], true, out); break;
+      default: conv5_row<8>(in, DP, D, wr, sb0[co], true, out); break;
     }
-#pragma unroll
-    for (int co = 0; co < 8; ++co) s_h1[(px * 8 + co) * DP + 2 + d] = fmaxf(o[co], 0.f);
   }
   __syncthreads();
-  // ---- conv1d 8->16 (k5) + ReLU ---------------------------------------------------------------
-  for (int item = tid; item < TX * D; item += CV_THREADS) {
-    const int px = item / D, d = item % D;
-    float o[16];
+  // ---- conv1d 8->16 (k5) + ReLU: thread = (pixel, output channel), TX * 16 = all 256 threads -------------------------------
+  {
+    const int px = tid >> 4, co = tid & 15;
+    float wr[8][5];
 #pragma unroll
-    for (int co = 0; co < 16; ++co) o[co] = sb1[co];
-    for (int ci = 0; ci < 8; ++ci) {
-      const float* src = s_h1 + (px * 8 + ci) * DP + d;
-      float t[5];
+    for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
-      for (int k = 0; k < 5; ++k) t[k] = src[k];
-#pragma unroll
-      for (int co = 0; co < 16; ++co)
-#pragma unroll
-        for (int k = 0; k < 5; ++k) o[co] = fmaf(sw1[(co * 8 + ci) * 5 + k], t[k], o[co]);
-    }
-#pragma unroll
-    for (int co = 0; co < 16; ++co) s_h2[(px * 16 + co) * DP + 2 + d] = fmaxf(o[co], 0.f);
+      for (int k = 0; k < 5; ++k) wr[ci][k] = sw1[(co * 8 + ci) * 5 + k];
+    conv5_row<8>(s_h1 + px * 8 * DP, DP, D, wr, sb1[co], true, s_h2 + (px * 16 + co) * DP);
   }
   __syncthreads();
-  // ---- conv1d 16->1 (k5) -> logits --------------------------------------------------------------
-  for (int item = tid; item < TX * D; item += CV_THREADS) {
-    const int px = item / D, d = item % D;
-    float o = sb2[0];
+  // ---- conv1d 16->1 (k5) -> logits: thread = (pixel, four disparities) ---------------------------------------------------
+  for (int item = tid; item < TX * ((D + 3) / 4); item += CV_THREADS) {
+    const int nd4 = (D + 3) / 4, px = item / nd4, d0 = (item % nd4) * 4;
+    float acc[4] = {sb2[0], sb2[0], sb2[0], sb2[0]};
+    const float* in = s_h2 + px * 16 * DP;
     for (int ci = 0; ci < 16; ++ci) {
-      const float* src = s_h2 + (px * 16 + ci) * DP + d;
+      const float4 a = *reinterpret_cast<const float4*>(in + ci * DP + d0);
+      const float4 b = *reinterpret_cast<const float4*>(in + ci * DP + d0 + 4);
+      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int k = 0; k < 5; ++k) o = fmaf(sw2[ci * 5 + k], src[k], o);
+      for (int k = 0; k < 5; ++k) {
+        const float wk = sw2[ci * 5 + k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fmaf(wk, v[j + k], acc[j]);
+      }
     }
-    s_lg[px * D + d] = o;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (d0 + j < D) s_lg[px * D + d0 + j] = acc[j];
   }
   __syncthreads();
 
-  // ---- softmax over D, 1-D NMS, top-K: one thread per pixel (D is small) ------------------------
-  if (tid < TX && x0 + tid < w) {
-    float* p = s_lg + tid * D;
-    const size_t pix = row_base + x0 + tid;
+  // ---- softmax over D, 1-D NMS, top-K: warp = pixel, lane holds d = lane + 32 j (D <= 128) -----------------------------------
+  for (int px = warp; px < ntx; px += CV_WARPS) {
+    const size_t pix = row_base + x0 + px;
+    const float* lg = s_lg + px * D;
+    float v[4];
     float m = -INFINITY;
-    for (int d = 0; d < D; ++d) m = fmaxf(m, p[d]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = lane + 32 * j;
+      v[j] = d < D ? lg[d] : -INFINITY;
+      m = fmaxf(m, v[j]);
+    }
+    m = warp_max(m);
     float sum = 0.f;
-    for (int d = 0; d < D; ++d) { const float e = expf(p[d] - m); p[d] = e; sum += e; }
-    for (int d = 0; d < D; ++d) { const float v = p[d] / sum; p[d] = v; prob_out[pix * D + d] = v; }
-    // NMS (max_pool1d k3 s1 p1, -inf padding): suppressed := eps. Done out-of-place via a
-    // rolling window so neighbours are compared on the un-suppressed values.
-    float prev = -INFINITY, cur = p[0];
-    for (int d = 0; d < D; ++d) {
-      const float nxt = (d + 1 < D) ? p[d + 1] : -INFINITY;
-      const float mx = fmaxf(fmaxf(prev, cur), nxt);
-      const float v = (cur != mx && cur > eps) ? eps : cur;
-      p[d] = v;
-      prev = cur; cur = nxt;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = lane + 32 * j;
+      v[j] = d < D ? expf(v[j] - m) : 0.f;
+      sum += v[j];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = lane + 32 * j;
+      v[j] = v[j] / sum;
+      if (d < D) prob_out[pix * D + d] = v[j];
+    }
+    // NMS (max_pool1d k3 s1 p1, -inf padding): suppressed := eps; neighbours are compared on the un-suppressed values
+    float nv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int d = lane + 32 * j;
+      float up = __shfl_up_sync(0xffffffffu, v[j], 1);        // d - 1
+      float dn = __shfl_down_sync(0xffffffffu, v[j], 1);      // d + 1
+      const float prev_chunk_last = __shfl_sync(0xffffffffu, j > 0 ? v[j > 0 ? j - 1 : 0] : 0.f, 31);
+      const float next_chunk_first = __shfl_sync(0xffffffffu, j < 3 ? v[j < 3 ? j + 1 : 3] : 0.f, 0);
+      if (lane == 0) up = j > 0 ? prev_chunk_last : -INFINITY;
+      if (lane == 31) dn = j < 3 ? next_chunk_first : -INFINITY;
+      if (d - 1 < 0) up = -INFINITY;
+      if (d + 1 >= D) dn = -INFINITY;
+      const float mx = fmaxf(fmaxf(up, v[j]), dn);
+      nv[j] = d < D ? ((v[j] != mx && v[j] > eps) ? eps : v[j]) : -INFINITY;
     }
     // top-K: value descending, index ascending among equals
     for (int k = 0; k < K; ++k) {
-      float best = -INFINITY; int bi = 0;
-      for (int d = 0; d < D; ++d) if (p[d] > best) { best = p[d]; bi = d; }
-      seeds[pix * K + k] = bi;
-      p[bi] = -INFINITY;
+      float best = -INFINITY;
+      int bi = 0x7fffffff;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = lane + 32 * j;
+        if (d < D && nv[j] > best) { best = nv[j]; bi = d; }     // ascending d inside a lane: strict > keeps the first
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) seeds[pix * K + k] = bi;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (lane + 32 * j == bi) nv[j] = -INFINITY;
     }
   }
 }
@@ -240,10 +352,12 @@ int cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int 
   NMRF_REQUIRE(C % 128 == 0 && C <= 512, "cost_volume_topk: C=%d must be a multiple of 128 (<=512)", C);
   NMRF_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, "cost_volume_topk: cost_group=%d unsupported", G);
   NMRF_REQUIRE(D >= 1 && D <= 128 && K >= 1 && K <= D, "cost_volume_topk: D=%d K=%d unsupported", D, K);
-  const int CS = C + 4, DP = D + 4;
-  const size_t featN = (size_t)(2 * TX + D - 1) * CS, hidN = (size_t)TX * 24 * DP;
-  const size_t smem = sizeof(float) * ((featN > hidN ? featN : hidN) + (size_t)TX * G * DP + (size_t)TX * D +
-                                       8 * G * 5 + 8 + 16 * 8 * 5 + 16 + 16 * 5 + 4);
+  NMRF_REQUIRE((reinterpret_cast<uintptr_t>(f1) & 15) == 0 && (reinterpret_cast<uintptr_t>(f2) & 15) == 0,
+               "cost_volume_topk: feature maps must be 16-byte aligned (TMA bulk copies)");
+  const int DP = (D + 4 + 3 + 3) & ~3;
+  const size_t featN = (size_t)(2 * TX + D - 1) * C, hidN = (size_t)TX * 24 * DP;
+  const size_t smem = sizeof(float) * ((featN > hidN ? featN : hidN) + (size_t)TX * G * DP +
+                                       (((size_t)TX * D + 3) & ~(size_t)3) + 8 * G * 5 + 8 + 16 * 8 * 5 + 16 + 16 * 5 + 4);
   NMRF_REQUIRE(smem <= 227 * 1024, "cost_volume_topk: C=%d D=%d needs %zu B of shared memory", C, D, smem);
   static PerDevice configured;
   ensure_dynamic_smem(cost_volume_topk_kernel, (int)smem, configured);

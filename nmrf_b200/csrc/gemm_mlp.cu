@@ -240,6 +240,25 @@ __device__ __forceinline__ void worker_tile(MSmem& sm, const nmrf_mlp_args& a, u
 #pragma unroll
     for (int c = 0; c < 8; ++c) dst[c] = make_float4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
   }
+  if (a.out_stats) {
+    // (mean, rstd) of the output row for the NEXT block's LayerNorm (nmrf_gemm_args.ln_stats): the row is in the registers of
+    // the quarter's four workers right now -- two-pass like ln_worker, through the same exchange buffer and named barrier
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += v[i];
+    sm.red[0][j][row] = s;
+    asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(128) : "memory");
+    const float mean = ((sm.red[0][0][row] + sm.red[0][1][row]) + (sm.red[0][2][row] + sm.red[0][3][row])) * (1.f / 128.f);
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; qq = fmaf(d, d, qq); }
+    sm.red[1][j][row] = qq;
+    asm volatile("bar.sync %0, %1;" ::"r"(8 + q), "r"(128) : "memory");
+    if (j == 0 && grow < a.rows) {
+      const float var = ((sm.red[1][0][row] + sm.red[1][1][row]) + (sm.red[1][2][row] + sm.red[1][3][row])) * (1.f / 128.f);
+      reinterpret_cast<float2*>(a.out_stats)[grow] = make_float2(mean, 1.f / sqrtf(var + 1e-5f));
+    }
+  }
   mtrace(tp, 3968 + it * 8 + 3);
 }
 

@@ -242,8 +242,18 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
       const bool row_ok = row0 + a_row < a.rows;
       float mean = 0.f, rstd = 1.f;
       if (LN) {
-        mbar_wait_warp(&sm.stats_full[it % G6_STATS], (it / G6_STATS) & 1);
-        mean = sm.mean[it % G6_STATS][a_row]; rstd = sm.rstd[it % G6_STATS][a_row];
+        if (a.ln_stats) {
+          // the kernel that wrote X also wrote each row's (mean, rstd) (nmrf_mlp_chain / nmrf_row_stats): 8 bytes per row
+          // instead of a statistics pass over the tile by the epilogue warps (which was the bottleneck of this kernel: ~13k
+          // cycles per tile, once per 128-column chunk, against ~6k cycles of MMA work)
+          if (row_ok) {
+            const float2 st = __ldg(reinterpret_cast<const float2*>(a.ln_stats) + row0 + a_row);
+            mean = st.x; rstd = st.y;
+          }
+        } else {
+          mbar_wait_warp(&sm.stats_full[it % G6_STATS], (it / G6_STATS) & 1);
+          mean = sm.mean[it % G6_STATS][a_row]; rstd = sm.rstd[it % G6_STATS][a_row];
+        }
       }
       for (int kb = 0; kb < nkb; ++kb, ++unit) {
         const int slot = unit % G6_NB;
@@ -369,13 +379,15 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
         if (lane == 0) mbar_arrive(&sm.stats_full[j % G6_STATS]);
       }
     };
-    if (LN) { stats(0); stats(1); stats(2); }
+    const bool own_stats = LN && a.ln_stats == nullptr;
+    if (own_stats) { stats(0); stats(1); stats(2); }
     int it = 0;
     uint32_t grp = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
       const int row0 = (t % n_rb) * G6_BM, n_base = (t / n_rb) * G6_BN;
-      // buffer (it+3) % 4 last held tile it-1, whose statistics the producers read before its MMAs, which this warp drained
-      if (LN) stats(it + 3);
+#ifdef NMRF_STATS_FIRST
+      if (own_stats) stats(it + 3);
+#endif
       trace(tp, 3584 + it * 4 + 0);
       const int nchunks = (min(G6_BN, a.N - n_base) + 31) / 32;
       // the tile's sum over its groups of k-blocks, in registers: this thread's row, column chunks half and half + 2 (32 columns each)
@@ -406,6 +418,12 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
         mbar_arrive(&sm.acc_empty[as]);
       }
       trace(tp, 3584 + it * 4 + 1);
+      // LayerNorm statistics three tiles ahead: AFTER this tile's accumulator stages have been handed back (the MMA warp is never
+      // more than three groups ahead of the drains).  Buffer (it+3) % 4 last held tile it-1, whose statistics the producers
+      // read before its MMAs, which this warp drained an iteration ago.
+#ifndef NMRF_STATS_FIRST
+      if (own_stats) stats(it + 3);
+#endif
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         const int ch = half + 2 * ci;
@@ -536,6 +554,46 @@ int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream) {
   }
   count_launch();
   return check_launch("token_gemm_tc6");
+}
+
+namespace {
+// (mean, rstd) of every 128-wide row: two-pass like torch's LayerNorm; 8 lanes per row, four rows per warp and step
+__global__ void __launch_bounds__(256) row_stats_kernel(const float* __restrict__ X, int ldx, int rows, float2* __restrict__ stats) {
+  const int lane = threadIdx.x & 31, g = lane >> 3, sub = lane & 7;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r0 = warp * 4; r0 < rows; r0 += nwarps * 4) {
+    const int r = r0 + g;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < rows) v[j] = *reinterpret_cast<const float4*>(X + (size_t)r * ldx + j * 32 + sub * 4);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+    const float mu = s * (1.f / 128.f);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float dx = v[j].x - mu, dy = v[j].y - mu, dz = v[j].z - mu, dw = v[j].w - mu;
+      q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+    }
+    q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+    if (sub == 0 && r < rows) stats[r] = make_float2(mu, 1.f / sqrtf(q * (1.f / 128.f) + 1e-5f));
+  }
+}
+}  // namespace
+
+int row_stats(const float* X, int ldx, int rows, float* stats, cudaStream_t stream) {
+  NMRF_REQUIRE(X && stats && rows >= 0 && ldx >= 128 && ldx % 4 == 0, "row_stats: bad arguments");
+  if (rows == 0) return NMRF_OK;
+  const int warps = (rows + 3) / 4;
+  const int blocks = min((warps + 7) / 8, 8 * nmrf::num_sms());
+  row_stats_kernel<<<blocks, 256, 0, stream>>>(X, ldx, rows, reinterpret_cast<float2*>(stats));
+  count_launch();
+  return check_launch("row_stats");
 }
 
 // N1 / N2: k x k convolution over NHWC as an implicit GEMM on the kernel above (CONV mode)

@@ -105,7 +105,7 @@ class _Gemm:
         a = GemmArgs()
         a.X, a.ldx, a.Kx = x_ptr, ldx, self.K
         a.E, a.lde, a.Ke, a.ediv = None, 0, 0, 1
-        a.ln_gamma, a.ln_beta = None, None
+        a.ln_gamma, a.ln_beta, a.ln_stats = None, None, None
         a.W, a.ldw = self._keep.data_ptr(), self._keep.stride(0)
         a.bias = self.bias.data_ptr() if self.bias is not None else None
         a.R, a.ldr = None, 0

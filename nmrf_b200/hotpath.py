@@ -171,7 +171,7 @@ class _Launches:
             self._splits[key] = (thi, tlo, W, Wc)
         return self._splits[key][:2]
 
-    def gemm(self, what, X, W, Y, rows, N, *, Kx=None, E=None, Ke=0, ediv=1, ln=None, bias=None, R=None, act=ACT_NONE):
+    def gemm(self, what, X, W, Y, rows, N, *, Kx=None, E=None, Ke=0, ediv=1, ln=None, bias=None, R=None, act=ACT_NONE, stats=None):
         Wt_hi = Wt_lo = None
         if self.tensor_cores and N % 16 == 0 and N <= 512 and W.is_cuda:
             Wt_hi, Wt_lo = self.tiles(W)
@@ -179,6 +179,7 @@ class _Launches:
         a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), (Kx if Kx is not None else X.shape[1])
         a.E, a.lde, a.Ke, a.ediv = (E.data_ptr() if E is not None else None), (E.stride(0) if E is not None else 0), Ke, ediv
         a.ln_gamma, a.ln_beta = (ln[0].data_ptr(), ln[1].data_ptr()) if ln is not None else (None, None)
+        a.ln_stats = stats.data_ptr() if (stats is not None and ln is not None) else None
         a.W, a.ldw = W.data_ptr(), W.stride(0)
         a.bias = bias.data_ptr() if bias is not None else None
         a.R, a.ldr = (R.data_ptr(), R.stride(0)) if R is not None else (None, 0)
@@ -186,13 +187,19 @@ class _Launches:
         a.rows, a.N, a.act = rows, N, act
         a.Wt_hi = Wt_hi.data_ptr() if Wt_hi is not None else None
         a.Wt_lo = Wt_lo.data_ptr() if Wt_lo is not None else None
-        self.keep(a, X, W, Wt_hi, Wt_lo, Y, E, ln, bias, R)
+        self.keep(a, X, W, Wt_hi, Wt_lo, Y, E, ln, bias, R, stats)
         # algorithmic work: 2*MAC flops; activations read+written once (weights are L2-resident, excluded)
         flops = 2.0 * rows * N * (a.Kx + Ke)
         nbytes = 4.0 * (rows * a.Kx + (rows // max(ediv, 1)) * Ke + rows * N * (2 if R is not None else 1))
         self.add(lib.nmrf_token_gemm, what, ctypes.byref(a), flops=flops, bytes=nbytes)
 
-    def block_tail(self, what, att, x, rows, proj_w, proj_b, n2, fc1_w, fc1_b, fc2_w, fc2_b):
+    def row_stats(self, what, X, rows, stats):
+        """(mean, rstd) of every row of X for the LayerNorm prologue of the GEMMs that read it (X written by a token GEMM; the
+        fused block tail writes the statistics of its output itself)"""
+        self.keep(X, stats)
+        self.add(lib.nmrf_row_stats, what, X.data_ptr(), X.stride(0), rows, stats.data_ptr(), bytes=4.0 * rows * 130)
+
+    def block_tail(self, what, att, x, rows, proj_w, proj_b, n2, fc1_w, fc1_b, fc2_w, fc2_b, stats=None):
         """x = x1 + Mlp(LN2(x1)), x1 = x + proj(att): ONE launch of nmrf_mlp_chain (SwinNMP / CSWinNMP tail, NMP.py:358-363,
         570-573).  The residual stream x stays in fp32 registers inside the kernel (gemm_mlp.cu: never in a tensor-core
         accumulator, whose round-toward-zero updates would bias it); NMRF_B200_RESIDUAL=identity (experiment) lets it ride the
@@ -213,7 +220,8 @@ class _Launches:
         a.Wstream, a.bias_mid, a.ln_gamma, a.ln_beta = ws.data_ptr(), proj_b.data_ptr(), n2[0].data_ptr(), n2[1].data_ptr()
         a.b1, a.bias_out = fc1_b.data_ptr(), bias_out.data_ptr()
         a.Y, a.ldy, a.rows, a.e_identity = x.data_ptr(), x.stride(0), rows, int(self.residual_preload)
-        self.keep(a, att, x, ws, bias_out, proj_b, n2, fc1_b)
+        a.out_stats = stats.data_ptr() if stats is not None else None
+        self.keep(a, att, x, ws, bias_out, proj_b, n2, fc1_b, stats)
         flops = 2.0 * rows * (128 * 128 + 2 * 128 * 512)
         self.add(lib.nmrf_mlp_chain, what, ctypes.byref(a), flops=flops, bytes=4.0 * rows * 128 * 3)
 
@@ -285,6 +293,7 @@ class HotPathPlan:
         self.x, self.att, self.h1, self.h2 = new(Tmax, 128), new(Tmax, 128), new(Tmax, 128), new(Tmax, 128)
         self.qkv, self.hid = new(Tmax, 384), new(Tmax, 512)
         self.feat, self.enc = new(Tmax, 160), new(Tmax, 32)
+        self.xstats = new(Tmax, 2)                              # (mean, rstd) of every row of x: the next LayerNorm's statistics
         self.cost48 = new(T8, 48)
         self.delta, self.score = new(Tmax, 64), new(Tmax, 64)
         self.pw = pw
@@ -303,10 +312,11 @@ class HotPathPlan:
         """proj + residual, then the Mlp block (NMP.py:358-363 / 570-573): one fused launch, or three token GEMMs"""
         if L_.mlp_chain:
             L_.block_tail(tag + ".tail", self.att, self.x, T, w["proj_w"], w["proj_b"], w["n2"], w["fc1_w"], w["fc1_b"],
-                          w["fc2_w"], w["fc2_b"])
+                          w["fc2_w"], w["fc2_b"], stats=self.xstats)
         else:
             L_.gemm(tag + ".proj", self.att, w["proj_w"], self.x, T, 128, bias=w["proj_b"], R=self.x)
             self._mlp_block(L_, T, w["n2"], w["fc1_w"], w["fc1_b"], w["fc2_w"], w["fc2_b"], tag)
+            L_.row_stats(tag + ".stats", self.x, T, self.xstats)
 
     def _build(self, pw):
         c, g, L_ = self.cfg, self.geom, self.launches
@@ -331,11 +341,13 @@ class HotPathPlan:
         L_.gemm("cost_encoder.0", self.cost48, pw.ce0_w, self.h1, T8, 128, bias=pw.ce0_b, act=ACT_GELU)
         L_.gemm("cost_encoder.2", self.h1, pw.ce2_w, self.h2, T8, 128, bias=pw.ce2_b)
         L_.gemm("propagation.proj", self.h2, pw.pproj_w, self.x, T8, 128, E=self.enc, Ke=32)
+        L_.row_stats("propagation.stats", self.x, T8, self.xstats)
         # A5+A6 -------------------------------------------------------------------------------------
         ctx = self.context.view(P8, 64)
         for i, w in enumerate(pw.prop_layers):
             t = f"prop{i}"
-            L_.gemm(t + ".qkv", self.x, w["qkv_w"], self.qkv, T8, 384, E=ctx, Ke=64, ediv=K, ln=w["n1"], bias=w["qkv_b"])
+            L_.gemm(t + ".qkv", self.x, w["qkv_w"], self.qkv, T8, 384, E=ctx, Ke=64, ediv=K, ln=w["n1"], bias=w["qkv_b"],
+                    stats=self.xstats)
             # stripe attention (A6): 2 heads x (q.k^T + p.v) x 32 dims over full-height and full-width stripes; qkv in, att out
             L_.add(lib.nmrf_stripe_attention, t + ".stripe", ptr(self.qkv), B, h8, w8, K, ptr(w["gv0"]), ptr(w["gv1"]),
                    ptr(self.att), bytes=4.0 * T8 * (384 + 128),
@@ -343,7 +355,7 @@ class HotPathPlan:
             self._block_tail(L_, T8, w, t)
         # A7 ----------------------------------------------------------------------------------------
         (w0, b0), (w1, b1), (w2, b2) = pw.prop_head
-        L_.gemm("prop_head.0", self.x, w0, self.h1, T8, 128, ln=pw.prop_norm, bias=b0, act=ACT_RELU)
+        L_.gemm("prop_head.0", self.x, w0, self.h1, T8, 128, ln=pw.prop_norm, bias=b0, act=ACT_RELU, stats=self.xstats)
         L_.gemm("prop_head.1", self.h1, w1, self.h2, T8, 128, bias=b1, act=ACT_RELU)
         L_.add(lib.nmrf_prop_head_tail, "prop_head.2", ptr(self.h2), ptr(w2), ptr(b2), ptr(self.seeds), T8, ptr(self.labels),
                optr(self.labels_lo), bytes=4.0 * T8 * 128 + 8.0 * T8 + 8.0 * T8)
@@ -354,11 +366,11 @@ class HotPathPlan:
         T8p = g["T8p"]
         (w0, b0), (w1, b1), (w2, b2) = pw.infer_head
         nrm = pw.stacks["inference"]["norm"]
-        L_.gemm("infer_head.0", self.x, w0, self.h1, T8p, 128, ln=nrm, bias=b0, act=ACT_RELU)
+        L_.gemm("infer_head.0", self.x, w0, self.h1, T8p, 128, ln=nrm, bias=b0, act=ACT_RELU, stats=self.xstats)
         L_.gemm("infer_head.1", self.h1, w1, self.h2, T8p, 128, bias=b1, act=ACT_RELU)
         L_.gemm("infer_head.2", self.h2, w2, self.delta, T8p, 64, bias=b2)
         # 0.25 * score (NMRF.py:220) does not change the argmax: the exact power-of-two scale is dropped
-        L_.gemm("infer_score_head", self.x, pw.score_head[0], self.score, T8p, 64, ln=nrm, bias=pw.score_head[1])
+        L_.gemm("infer_score_head", self.x, pw.score_head[0], self.score, T8p, 64, ln=nrm, bias=pw.score_head[1], stats=self.xstats)
         L_.add(lib.nmrf_select_median, "select_median", ptr(self.delta), ptr(self.score), ptr(self.labels), optr(self.labels_lo),
                B, h8, w8, K, g["Hp8"], g["Wp8"], g["top8"], g["left8"], ptr(self.disp_curr), optr(self.disp_curr_lo),
                bytes=4.0 * (2 * T8 * 64 + 2 * T8 + 2 * g["P4"]))
@@ -370,7 +382,7 @@ class HotPathPlan:
         T4p = g["T4p"]
         (w0, b0), (w1, b1), (w2, b2) = pw.refine_head
         nrm = pw.stacks["refinement"]["norm"]
-        L_.gemm("refine_head.0", self.x, w0, self.h1, T4p, 128, ln=nrm, bias=b0, act=ACT_RELU)
+        L_.gemm("refine_head.0", self.x, w0, self.h1, T4p, 128, ln=nrm, bias=b0, act=ACT_RELU, stats=self.xstats)
         L_.gemm("refine_head.1", self.h1, w1, self.h2, T4p, 128, bias=b1, act=ACT_RELU)
         delta16 = self.delta.view(-1)[:T4p * 16].view(T4p, 16)      # dense [T4p,16] as nmrf_refine_tail expects
         L_.gemm("refine_head.2", self.h2, w2, delta16, T4p, 16, bias=b2)
@@ -392,16 +404,19 @@ class HotPathPlan:
         if Hp != h or Wp != w:
             L_.add(lib.nmrf_zero_pad_rows, name + ".zero_pad", ptr(self.x), B, h, w, K, Hp, Wp, top, left,
                    bytes=4.0 * 128 * (Tp - B * h * w * K))
+        L_.row_stats(name + ".stats", self.x, Tp, self.xstats)
         for i, wt in enumerate(S["layers"]):
             t = f"{name}{i}"
             shift = 0 if i % 2 == 0 else ws // 2                     # NMRF.py:72,96
             if with_self:
                 L_.gemm(t + ".self.qkv", self.x, wt["s_qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["s_n1"],
-                        bias=wt["s_qkv_b"])
+                        bias=wt["s_qkv_b"], stats=self.xstats)
                 L_.add(lib.nmrf_proposal_attention, t + ".self.attn", ptr(self.qkv), Tp // K, K, ptr(self.att),
                        bytes=4.0 * Tp * (384 + 128), flops=2.0 * (Tp // K) * 4 * K * K * 32 * 2)
                 L_.gemm(t + ".self.proj", self.att, wt["s_proj_w"], self.x, Tp, 128, bias=wt["s_proj_b"], R=self.x)
-            L_.gemm(t + ".qkv", self.x, wt["qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["n1"], bias=wt["qkv_b"])
+                L_.row_stats(t + ".self.stats", self.x, Tp, self.xstats)
+            L_.gemm(t + ".qkv", self.x, wt["qkv_w"], self.qkv, Tp, 384, E=self.enc, Ke=32, ln=wt["n1"], bias=wt["qkv_b"],
+                    stats=self.xstats)
             # window attention (A11): 4 heads x 5 contractions of (ws^2 K)^2 x 32 per window (q.k, q.Rk, k.Rq, A.v, A.Rv; H4)
             L_.add(lib.nmrf_window_attention, t + ".window", ptr(self.qkv), ptr(wt["table"]), B, Hp, Wp, K, ws, shift,
                    1 if with_self else 0, ptr(self.att), bytes=4.0 * Tp * (384 + 128),

@@ -68,7 +68,16 @@ def pack_weight_tiles(W):
 
 
 @_on_device
-def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, Wt=None):
+def row_stats(X):
+    """(mean, rstd) of every row of X [rows, 128] (LayerNorm statistics, eps 1e-5) -> [rows, 2]"""
+    _chk(X, "X")
+    st = torch.empty(X.shape[0], 2, device=X.device)
+    _lib.check(lib.nmrf_row_stats(X.data_ptr(), X.stride(0), X.shape[0], st.data_ptr(), _stream()), "row_stats")
+    return st
+
+
+@_on_device
+def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=None, Wt=None, ln_stats=None):
     """Y = act(concat(LN?(X), E[r // ediv]) @ W.T + bias) (+ R).  X [rows,Kx], E [*,Ke], W [N,>=Kx+Ke].
     With Wt = pack_weight_tiles(W) the tcgen05 3xTF32 kernel is used, otherwise the exact-fp32 FMA kernel."""
     for n, t in (("X", X), ("W", W), ("E", E), ("bias", bias), ("R", R)):
@@ -80,6 +89,7 @@ def token_gemm(X, W, *, E=None, ediv=1, ln=None, bias=None, R=None, act=0, out=N
     a.X, a.ldx, a.Kx = X.data_ptr(), X.stride(0), Kx
     a.E, a.lde, a.Ke, a.ediv = _p(E), (E.stride(0) if E is not None else 0), (E.shape[1] if E is not None else 0), ediv
     a.ln_gamma, a.ln_beta = (_p(ln[0]), _p(ln[1])) if ln is not None else (None, None)
+    a.ln_stats = _p(ln_stats)
     a.W, a.ldw = W.data_ptr(), W.stride(0)
     a.bias = _p(bias)
     a.R, a.ldr = _p(R), (R.stride(0) if R is not None else 0)
@@ -119,7 +129,7 @@ def pack_mlp_stream(W1cat, Wfc1, Wfc2):
 
 
 @_on_device
-def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_identity=False):
+def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_identity=False, out_stats=None):
     """Y = x1 + (fc2(GELU(fc1(LN(x1)))) + bias_out) (bias_out = b_fc2) with x1 = E + (X @ W1.T + bias_mid) (e_identity: E is the
     residual, kept in fp32 registers) or x1 = concat(X, E) @ W1cat.T + bias_mid; wstream from pack_mlp_stream(W1 or W1cat, ...).
     `out` may alias E."""
@@ -138,6 +148,7 @@ def mlp_chain(X, wstream, bias_mid, ln, b1, bias_out, *, E=None, out=None, e_ide
     a.Wstream, a.bias_mid, a.ln_gamma, a.ln_beta = wstream.data_ptr(), bias_mid.data_ptr(), ln[0].data_ptr(), ln[1].data_ptr()
     a.b1, a.bias_out = b1.data_ptr(), bias_out.data_ptr()
     a.Y, a.ldy, a.rows, a.e_identity = Y.data_ptr(), Y.stride(0), rows, int(e_identity)
+    a.out_stats = _p(out_stats)
     _lib.check(lib.nmrf_mlp_chain(ctypes.byref(a), _stream()), "mlp_chain")
     return Y
 

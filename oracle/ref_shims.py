@@ -30,100 +30,17 @@ def reference_available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "nmrf", "models"))
 
 
-class _Mlp(nn.Module):
-    """timm 0.9.16 `Mlp` forward restated: fc1 -> act -> drop1 -> fc2 -> drop2."""
-
-    def __init__(self, in_features, hidden_features=None, out_features=None,
-                 act_layer=nn.GELU, bias=True, drop=0.0, **_):
-        super().__init__()
-        out_features = out_features or in_features
-        hidden_features = hidden_features or in_features
-        self.fc1 = nn.Linear(in_features, hidden_features, bias=bias)
-        self.act = act_layer()
-        self.drop1 = nn.Dropout(drop)
-        self.fc2 = nn.Linear(hidden_features, out_features, bias=bias)
-        self.drop2 = nn.Dropout(drop)
-
-    def forward(self, x):
-        return self.drop2(self.fc2(self.drop1(self.act(self.fc1(x)))))
-
-
-class _DropPath(nn.Module):
-    def __init__(self, drop_prob=0.0, scale_by_keep=True):
-        super().__init__()
-        self.drop_prob = drop_prob
-
-    def forward(self, x):
-        if self.drop_prob == 0.0 or not self.training:
-            return x
-        raise NotImplementedError("DropPath in training mode is out of scope")
-
-
-def _to_2tuple(x):
-    return tuple(x) if isinstance(x, (tuple, list)) else (x, x)
-
-
-class _CfgNode(dict):
-    """Just enough of yacs.config.CfgNode for `nmrf.config` to import."""
-
-    def __init__(self, init_dict=None, key_list=None, new_allowed=False):
-        super().__init__(init_dict or {})
-
-    def __getattr__(self, name):
-        try:
-            return self[name]
-        except KeyError:
-            raise AttributeError(name)
-
-    def __setattr__(self, name, value):
-        self[name] = value
-
-    def clone(self):
-        import copy
-        return copy.deepcopy(self)
+from nmrf_b200.ref_compat import _CfgNode, _DropPath, _Mlp, _to_2tuple, install_missing  # noqa: E402,F401  (shared stand-ins)
 
 
 def install():
-    """Install the shims into sys.modules and put the reference on sys.path."""
+    """Install the stand-ins into sys.modules, put the reference on sys.path, and route its MultiScaleDeformableAttention
+    extension to the reference's own pure-PyTorch implementation."""
     if not reference_available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
     if "nmrf_ref_shims_installed" in sys.modules:
         return
-    layers = types.ModuleType("timm.models.layers")
-    layers.Mlp = _Mlp
-    layers.DropPath = _DropPath
-    layers.to_2tuple = _to_2tuple
-    layers.trunc_normal_ = torch.nn.init.trunc_normal_
-    timm = types.ModuleType("timm")
-    timm_models = types.ModuleType("timm.models")
-    timm_layers = types.ModuleType("timm.layers")
-    for k in ("Mlp", "DropPath", "to_2tuple", "trunc_normal_"):
-        setattr(timm_layers, k, getattr(layers, k))
-    timm.models = timm_models
-    timm.layers = timm_layers
-    timm_models.layers = layers
-    sys.modules.setdefault("timm", timm)
-    sys.modules.setdefault("timm.models", timm_models)
-    sys.modules.setdefault("timm.models.layers", layers)
-    sys.modules.setdefault("timm.layers", timm_layers)
-
-    yacs = types.ModuleType("yacs")
-    yacs_config = types.ModuleType("yacs.config")
-    yacs_config.CfgNode = _CfgNode
-    yacs.config = yacs_config
-    sys.modules.setdefault("yacs", yacs)
-    sys.modules.setdefault("yacs.config", yacs_config)
-
-    omegaconf = types.ModuleType("omegaconf")
-
-    class DictConfig(dict):
-        pass
-
-    omegaconf.DictConfig = DictConfig
-    sys.modules.setdefault("omegaconf", omegaconf)
-
-    sys.modules.setdefault("imageio", types.ModuleType("imageio"))
-
+    install_missing()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
 

@@ -51,9 +51,9 @@ def test_struct_layout_matches_c():
     from nmrf_b200 import _lib
     assert ctypes.sizeof(_lib.SeedWeights) == 6 * 8
     # X,ldx,Kx | E,lde,Ke,ediv | g,b | W,ldw | bias | R,ldr | Y,ldy | rows,N,act
-    assert ctypes.sizeof(_lib.GemmArgs) == 136
+    assert ctypes.sizeof(_lib.GemmArgs) == 144
     # X,ldx,Kx | E,lde,Ke | Wstream | bias_mid | g,b | b1 | bias_out | Y,ldy,rows | e_identity (+pad)
-    assert ctypes.sizeof(_lib.MlpArgs) == 104
+    assert ctypes.sizeof(_lib.MlpArgs) == 112
 
 
 def test_struct_field_offsets_match_a_c_compiler(tmp_path):

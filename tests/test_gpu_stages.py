@@ -124,6 +124,36 @@ def test_mlp_chain(ops, rows, mode):
         assert rel_err(xe, ref) <= 1e-5
 
 
+def test_row_stats_and_external_layernorm_statistics(ops):
+    """nmrf_row_stats / nmrf_mlp_chain(out_stats) hand the next LayerNorm its (mean, rstd): the token GEMM that takes them
+    (nmrf_gemm_args.ln_stats) must give what it gives when it computes the statistics itself"""
+    g = torch.Generator().manual_seed(12)
+    rows = 128 * 3 + 77
+    X = 2.0 * torch.randn(rows, 128, generator=g) + 0.5
+    st = ops.row_stats(cuda(X))
+    mean, var = X.double().mean(1), X.double().var(1, unbiased=False)
+    assert float((st[:, 0].cpu().double() - mean).abs().max()) <= 1e-6
+    assert float((st[:, 1].cpu().double() * (var + 1e-5).sqrt() - 1).abs().max()) <= 2e-6
+    W = torch.randn(384, 160, generator=g) / 160 ** 0.5
+    E = torch.randn(rows, 32, generator=g)
+    gam, bet = 1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
+    kw = dict(E=cuda(E), ln=(cuda(gam), cuda(bet)), Wt=ops.pack_weight_tiles(cuda(W)))
+    own = ops.token_gemm(cuda(X), cuda(W), **kw)
+    ext = ops.token_gemm(cuda(X), cuda(W), ln_stats=st, **kw)
+    ref = torch.cat([torch.nn.functional.layer_norm(X.double(), (128,), gam.double(), bet.double(), 1e-5), E.double()], 1) @ W.double().T
+    assert rel_err(ext, ref) <= 4e-6 and rel_err(own, ref) <= 4e-6
+    assert rel_err(ext, own) <= 1e-6
+    # the fused block tail writes the statistics of ITS output
+    att = torch.randn(rows, 128, generator=g)
+    Wp, W1, W2 = (torch.randn(128, 128, generator=g) / 11.3, torch.randn(512, 128, generator=g) / 11.3, torch.randn(128, 512, generator=g) / 22.6)
+    z128, z512, one = torch.zeros(128), torch.zeros(512), torch.ones(128)
+    ws = ops.pack_mlp_stream(cuda(Wp), cuda(W1), cuda(W2))
+    stats = torch.zeros(rows, 2, device=DEV)
+    y = ops.mlp_chain(cuda(att), ws, cuda(z128), (cuda(one), cuda(z128)), cuda(z512), cuda(z128), E=cuda(X), e_identity=True, out_stats=stats)
+    st2 = ops.row_stats(y)
+    assert float((stats[:, 0] - st2[:, 0]).abs().max()) <= 1e-6 and float((stats[:, 1] / st2[:, 1] - 1).abs().max()) <= 2e-6
+
+
 def test_token_gemm_rejects_bad_arguments(ops):
     with pytest.raises(RuntimeError, match="multiple"):
         ops.token_gemm(torch.zeros(8, 100, device=DEV), torch.zeros(128, 100, device=DEV))

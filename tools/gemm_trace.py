@@ -16,18 +16,17 @@ for name, rows, Kx, Ke, N, ln, act, res in [("fc2", 34560, 512, 0, 128, False, 0
     X = torch.randn(rows, Kx, generator=g).to(dev)
     E = torch.randn(rows, Ke, generator=g).to(dev) if Ke else None
     W = (torch.randn(N, Kx + Ke, generator=g) / (Kx + Ke) ** 0.5).to(dev)
-    hi, lo = ops.split_tf32(W)
     Wt = ops.pack_weight_tiles(W)
     b = torch.randn(N, generator=g).to(dev)
     gam, bet = torch.ones(Kx, device=dev), torch.zeros(Kx, device=dev)
     R = torch.randn(rows, N, generator=g).to(dev) if res else None
-    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, W_lo=lo, Wt=Wt)
+    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, Wt=Wt)
     for _ in range(3):
-        ops.token_gemm(X, hi, **kw)
+        ops.token_gemm(X, W, **kw)
     tr = torch.zeros(4096, dtype=torch.int64, device=dev)
     _lib.check(_lib.lib.nmrf_debug_set_trace(tr.data_ptr()), "set_trace")
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record(); ops.token_gemm(X, hi, **kw); e.record(); torch.cuda.synchronize()
+    s.record(); ops.token_gemm(X, W, **kw); e.record(); torch.cuda.synchronize()
     _lib.check(_lib.lib.nmrf_debug_set_trace(None), "set_trace")
     t = tr.cpu().tolist()
     t0 = min(v for v in t if v > 0)

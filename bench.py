@@ -253,7 +253,7 @@ def main():
     w = WORKLOAD
     B, H, W, K, steps, warmup = w["B"], w["H"], w["W"], w["K"], args.steps, max(args.warmup, 3)
     model, sd = build_model(dev)
-    runner = GraphedNMRF(model, B, H, W)
+    runner = GraphedNMRF(model, B, H, W, graph_full=not w.get("swin"))
     plan = runner.plan
     # distinct pairs per rank (weak scaling: every rank processes its own pairs)
     host = [tuple(t.pin_memory() for t in synthetic_pair(B, H, W, w["max_disp"], rank * N_PAIRS + i)) for i in range(N_PAIRS)]

@@ -12,27 +12,95 @@ constexpr int CV_WARPS = CV_THREADS / 32;
 
 __device__ __forceinline__ uint32_t cv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// conv1d (kernel 5, padding 2) over D for one (pixel, output channel): `in` = the pixel's CI input rows in shared memory (row
-// stride DP floats, value d at position d + 2, zeros around it), 5 CI weights in registers.  Four outputs per step from two
-// aligned 16-byte loads per input row (20 FMAs per 2 loads; the round-1 kernel read one weight from shared memory per FMA).
+// Row layout of every conv1d operand in shared memory: value d at position d + 4, zeros elsewhere (the padding of the k = 5
+// convolution), row stride DP floats with DP / 4 odd -- so that the float4 stores of 32 threads (32 different rows) hit 32
+// different bank groups, and a chunk of four outputs d0 .. d0+3 reads its eight taps (positions d0+2 .. d0+9) as 8 + 16 + 8 bytes.
+__host__ __device__ __forceinline__ int cv_row_stride(int D) {
+  int dp = (D + 10 + 3) & ~3;
+  if (((dp >> 2) & 1) == 0) dp += 4;
+  return dp;
+}
+
+// conv1d (kernel 5, padding 2) over D for one (pixel, output channel): `in` = the pixel's CI input rows, 5 CI weights in
+// registers.  Four outputs per step from three aligned loads per input row (20 FMAs per 3 loads; the round-1 kernel read one
+// weight from shared memory per FMA).  Chunks d0 = 4 * c for c in [c_begin, c_end).
 template <int CI>
-__device__ __forceinline__ void conv5_row(const float* __restrict__ in, int DP, int D, const float (&w)[CI][5], float bias, bool relu,
-                                          float* __restrict__ out /* row, position d + 2 */) {
-  for (int d0 = 0; d0 < D; d0 += 4) {
+__device__ __forceinline__ void conv5_row(const float* __restrict__ in, int DP, int c_begin, int c_end, const float (&w)[CI][5], float bias,
+                                          bool relu, float* __restrict__ out /* row */) {
+  for (int cch = c_begin; cch < c_end; ++cch) {
+    const int d0 = cch * 4;
     float acc[4] = {bias, bias, bias, bias};
 #pragma unroll
     for (int ci = 0; ci < CI; ++ci) {
-      const float4 a = *reinterpret_cast<const float4*>(in + ci * DP + d0);
-      const float4 b = *reinterpret_cast<const float4*>(in + ci * DP + d0 + 4);
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};          // positions d0 .. d0+7 = taps d0-2 .. d0+5
+      const float* r = in + ci * DP + d0;
+      const float2 a = *reinterpret_cast<const float2*>(r + 2);
+      const float4 b = *reinterpret_cast<const float4*>(r + 4);
+      const float2 c = *reinterpret_cast<const float2*>(r + 8);
+      const float v[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};          // positions d0+2 .. d0+9 = taps d0-2 .. d0+5
 #pragma unroll
       for (int k = 0; k < 5; ++k)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[j] = fmaf(w[ci][k], v[j + k], acc[j]);
     }
+    if (relu) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (d0 + j < D) out[2 + d0 + j] = relu ? fmaxf(acc[j], 0.f) : acc[j];
+      for (int j = 0; j < 4; ++j) acc[j] = fmaxf(acc[j], 0.f);
+    }
+    // positions 4 + d0 .. + 3: 16-byte aligned.  Outputs past D land in the row's zero tail: the caller re-zeroes it (D % 4 != 0)
+    *reinterpret_cast<float4*>(out + 4 + d0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  }
+}
+
+// A1 for one pixel: lane l owns the float4 channel chunks l + 32 j (j < NJ = C / 128): a warp's 16-byte loads cover 512
+// contiguous bytes (no bank conflicts; a blocked channel split reads with a 32-byte lane stride: 2-way).  Chunk l + 32 j
+// belongs to group (l + 32 j) / (C / (4 G)): the group sums are xor-shuffle reductions over LG = min(32, C / (4 G)) lanes.
+template <int NJ>
+__device__ __forceinline__ void corr_pixel(const float* __restrict__ s_f1, const float* __restrict__ s_f2, float* __restrict__ s_cv,
+                                           int px, int x, int C, int G, int D, int DP, int lane) {
+  const int cpg4 = C / (4 * G);                 // float4 chunks per group
+  const int LG = cpg4 < 32 ? cpg4 : 32;         // lanes that share a group within one 32-chunk slab
+  const float inv = 1.f / (float)(C / G);
+  float4 a[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) a[j] = *reinterpret_cast<const float4*>(s_f1 + px * C + (lane + 32 * j) * 4);
+  for (int d0 = 0; d0 < D; d0 += 4) {           // four disparities in flight
+    float s[4][NJ];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int d = min(d0 + e, D - 1);
+      const float* b = s_f2 + (size_t)(px + (D - 1) - d) * C + lane * 4;
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        const float4 vb = *reinterpret_cast<const float4*>(b + 128 * j);
+        s[e][j] = fmaf(a[j].x, vb.x, fmaf(a[j].y, vb.y, fmaf(a[j].z, vb.z, a[j].w * vb.w)));
+      }
+    }
+    if (cpg4 >= 32) {                           // whole slabs belong to one group: add the slabs of a group first
+      const int spg = cpg4 / 32;                // slabs per group
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j)
+          if (j % spg != 0) s[e][j - j % spg] += s[e][j];
+    }
+    for (int o = LG >> 1; o > 0; o >>= 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) s[e][j] += __shfl_xor_sync(0xffffffffu, s[e][j], o);
+    }
+    if ((lane % LG) == 0) {
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        if (cpg4 >= 32 && (j % (cpg4 / 32)) != 0) continue;
+        const int g = (lane + 32 * j) / cpg4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int d = d0 + e;
+          if (d < D) s_cv[(px * G + g) * DP + 4 + d] = (x >= d) ? s[e][j] * inv : 0.f;
+        }
+      }
+    }
   }
 }
 
@@ -40,9 +108,9 @@ __device__ __forceinline__ void conv5_row(const float* __restrict__ in, int DP, 
 // CTAs share an SM).  HBM sees every byte about once and nothing between the two feature maps and the outputs leaves the SM:
 //   stage   the f1 tile (TX pixels) and the f2 tile with its D-1 halo are each ONE contiguous run of an NHWC row: two TMA
 //           bulk copies (cp.async.bulk -> mbarrier), no per-thread loads;
-//   A1      group-wise correlation: warp = pixel, lane = C/32 channels; f1 stays in registers over d, the G group sums come
-//           from xor-shuffles; the [TX,G,D] slab is assembled in shared memory and leaves as ONE contiguous run of
-//           cost_volume (16-byte coalesced stores), not as scattered 4-byte stores;
+//   A1      group-wise correlation: warp = pixel, lane = interleaved 16-byte channel chunks (corr_pixel); f1 stays in registers
+//           over d, the G group sums come from xor-shuffles; the [TX,G,D] slab is assembled in shared memory and leaves as ONE
+//           contiguous run of cost_volume (16-byte coalesced stores), not as scattered 4-byte stores;
 //   A2      conv1d G->8->16->1: thread = (pixel, output channel), its 5 CI weights in registers, four d per step (conv5_row);
 //           softmax, 1-D NMS and top-K: WARP per pixel, lane = d, shuffles (the round-1 kernel ran them on 32 threads of
 //           the CTA, serially over D).
@@ -55,7 +123,8 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
                         float* __restrict__ cost_volume, float* __restrict__ prob_out,
                         int64_t* __restrict__ seeds) {
   extern __shared__ __align__(128) float smem[];
-  const int DP = (D + 4 + 3 + 3) & ~3;       // row stride: value d at d + 2, zeros elsewhere; loads reach d0 + 7 <= roundup(D,4) + 3
+  const int DP = cv_row_stride(D);
+  const int nch = (D + 3) >> 2;              // chunks of four disparities
   const int featN = (2 * TX + D - 1) * C, hidN = TX * 24 * DP;
   float* s_f1 = smem;                        // TX*C
   float* s_f2 = s_f1 + TX * C;               // (TX+D-1)*C
@@ -108,78 +177,47 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
   }
   __syncthreads();
 
-  // ---- A1: group-wise correlation.  warp = pixel (TX / 8 pixels per warp), lane = C/32 consecutive channels; a group is
-  //      32/G consecutive lanes.  Pixels left of the image (x < d) read whatever the halo holds: their value is SELECTED to 0.
-  {
-    const int cpl = C / 32;                       // channels per lane: 4 (C=128), 8 (C=256), 16 (C=512)
-    const int lpg = 32 / G;                       // lanes per group
-    const float inv = 1.f / (float)(C / G);
-    const int g = lane / lpg;
-    for (int px = warp; px < ntx; px += CV_WARPS) {
-      const int x = x0 + px;
-      float a[16];
-#pragma unroll
-      for (int c = 0; c < 16; c += 4)
-        if (c < cpl) *reinterpret_cast<float4*>(a + c) = *reinterpret_cast<const float4*>(s_f1 + px * C + lane * cpl + c);
-      for (int d0 = 0; d0 < D; d0 += 4) {         // four disparities in flight
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int d = min(d0 + j, D - 1);
-          const float* b = s_f2 + (size_t)(px + (D - 1) - d) * C + lane * cpl;
-#pragma unroll
-          for (int c = 0; c < 16; c += 4)
-            if (c < cpl) {
-              const float4 vb = *reinterpret_cast<const float4*>(b + c);
-              s[j] = fmaf(a[c], vb.x, s[j]); s[j] = fmaf(a[c + 1], vb.y, s[j]);
-              s[j] = fmaf(a[c + 2], vb.z, s[j]); s[j] = fmaf(a[c + 3], vb.w, s[j]);
-            }
-        }
-        for (int o = lpg >> 1; o > 0; o >>= 1) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-        }
-        if ((lane % lpg) == 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int d = d0 + j;
-            if (d < D) {
-              const float v = (x >= d) ? s[j] * inv : 0.f;
-              s_cv[(px * G + g) * DP + 2 + d] = v;
-            }
-          }
-        }
-      }
+  // ---- A1: group-wise correlation, warp = pixel (TX / 8 pixels per warp).  Pixels left of the image (x < d) read whatever the
+  //      halo holds: their value is SELECTED to 0.
+  for (int px = warp; px < ntx; px += CV_WARPS) {
+    switch (C >> 7) {
+      case 1: corr_pixel<1>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
+      case 2: corr_pixel<2>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
+      case 3: corr_pixel<3>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
+      default: corr_pixel<4>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
     }
   }
   __syncthreads();
   // the tile's [ntx, G, D] slab is one contiguous run of cost_volume: coalesced 16-byte stores, consecutive threads ->
-  // consecutive addresses (a (pixel, group) row of D floats sits at offset 2 of its shared-memory row: two 8-byte reads)
+  // consecutive addresses (a (pixel, group) row of D floats sits at position 4 of its shared-memory row)
   {
     float* dst = cost_volume + (row_base + x0) * G * D;
     if ((D & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       const int q4 = D >> 2, n4 = ntx * G * q4;
       for (int i = tid; i < n4; i += CV_THREADS) {
         const int r = i / q4, q = i - r * q4;
-        const float2 lo = *reinterpret_cast<const float2*>(s_cv + r * DP + 2 + q * 4);
-        const float2 hi = *reinterpret_cast<const float2*>(s_cv + r * DP + 4 + q * 4);
-        reinterpret_cast<float4*>(dst)[i] = make_float4(lo.x, lo.y, hi.x, hi.y);
+        reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(s_cv + r * DP + 4 + q * 4);
       }
     } else {
-      for (int i = tid; i < ntx * G * D; i += CV_THREADS) dst[i] = s_cv[(i / D) * DP + 2 + i % D];
+      for (int i = tid; i < ntx * G * D; i += CV_THREADS) dst[i] = s_cv[(i / D) * DP + 4 + i % D];
     }
   }
-  // features are dead: zero the halos of h1 | h2 (value d lives at d + 2; everything else in a row must read as zero padding)
-  for (int r = tid; r < TX * 24; r += CV_THREADS) {
-    float* row = s_h1 + r * DP;
-    row[0] = 0.f; row[1] = 0.f;
-    for (int i = D + 2; i < DP; ++i) row[i] = 0.f;
-  }
+  // features are dead: zero the halos of h1 | h2 (value d lives at d + 4; everything else in a row must read as zero padding)
+  auto zero_halo = [&](float* rows, int nrows, bool left) {
+    for (int r = tid; r < nrows; r += CV_THREADS) {
+      float* row = rows + r * DP;
+      if (left) *reinterpret_cast<float4*>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = D + 4; i < DP; ++i) row[i] = 0.f;
+    }
+  };
+  zero_halo(s_h1, TX * 24, true);
   __syncthreads();
 
-  // ---- A2: conv1d G->8 (k5) + ReLU: thread = (pixel, output channel) ---------------------------------------------------
-  if (tid < TX * 8) {
-    const int px = tid >> 3, co = tid & 7;
+  // ---- A2: conv1d G->8 (k5) + ReLU: thread = (pixel, output channel, half of the disparity chunks) ------------------------
+  {
+    const int item = tid & (TX * 8 - 1), half = tid / (TX * 8);       // TX * 8 = 128 items, two threads each
+    const int px = item >> 3, co = item & 7;
+    const int cb = half ? (nch + 1) / 2 : 0, ce = half ? nch : (nch + 1) / 2;
     float wr[8][5];
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci)
@@ -188,13 +226,14 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
     const float* in = s_cv + px * G * DP;
     float* out = s_h1 + (px * 8 + co) * DP;
     switch (G) {                                   // the input-channel count is a loop bound of fully unrolled code
-      case 1: conv5_row<1>(in, DP, D, reinterpret_cast<const float(&)[1][5]>(wr), sb0[co], true, out); break;
-      case 2: conv5_row<2>(in, DP, D, reinterpret_cast<const float(&)[2][5]>(wr), sb0[co], true, out); break;
-      case 4: conv5_row<4>(in, DP, D, reinterpret_cast<const float(&)[4][5]>(wr), sb0[co], true, out); break;
-      default: conv5_row<8>(in, DP, D, wr, sb0[co], true, out); break;
+      case 1: conv5_row<1>(in, DP, cb, ce, reinterpret_cast<const float(&)[1][5]>(wr), sb0[co], true, out); break;
+      case 2: conv5_row<2>(in, DP, cb, ce, reinterpret_cast<const float(&)[2][5]>(wr), sb0[co], true, out); break;
+      case 4: conv5_row<4>(in, DP, cb, ce, reinterpret_cast<const float(&)[4][5]>(wr), sb0[co], true, out); break;
+      default: conv5_row<8>(in, DP, cb, ce, wr, sb0[co], true, out); break;
     }
   }
   __syncthreads();
+  if (D & 3) { zero_halo(s_h1, TX * 8, false); __syncthreads(); }      // a chunk wrote past D into the zero tail
   // ---- conv1d 8->16 (k5) + ReLU: thread = (pixel, output channel), TX * 16 = all 256 threads -------------------------------
   {
     const int px = tid >> 4, co = tid & 15;
@@ -203,18 +242,21 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
     for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
       for (int k = 0; k < 5; ++k) wr[ci][k] = sw1[(co * 8 + ci) * 5 + k];
-    conv5_row<8>(s_h1 + px * 8 * DP, DP, D, wr, sb1[co], true, s_h2 + (px * 16 + co) * DP);
+    conv5_row<8>(s_h1 + px * 8 * DP, DP, 0, nch, wr, sb1[co], true, s_h2 + (px * 16 + co) * DP);
   }
   __syncthreads();
+  if (D & 3) { zero_halo(s_h2, TX * 16, false); __syncthreads(); }
   // ---- conv1d 16->1 (k5) -> logits: thread = (pixel, four disparities) ---------------------------------------------------
-  for (int item = tid; item < TX * ((D + 3) / 4); item += CV_THREADS) {
-    const int nd4 = (D + 3) / 4, px = item / nd4, d0 = (item % nd4) * 4;
+  for (int item = tid; item < TX * nch; item += CV_THREADS) {
+    const int px = item / nch, d0 = (item % nch) * 4;
     float acc[4] = {sb2[0], sb2[0], sb2[0], sb2[0]};
-    const float* in = s_h2 + px * 16 * DP;
+    const float* in = s_h2 + px * 16 * DP + d0;
     for (int ci = 0; ci < 16; ++ci) {
-      const float4 a = *reinterpret_cast<const float4*>(in + ci * DP + d0);
-      const float4 b = *reinterpret_cast<const float4*>(in + ci * DP + d0 + 4);
-      const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const float* r = in + ci * DP;
+      const float2 a = *reinterpret_cast<const float2*>(r + 2);
+      const float4 b = *reinterpret_cast<const float4*>(r + 4);
+      const float2 c = *reinterpret_cast<const float2*>(r + 8);
+      const float v[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
         const float wk = sw2[ci * 5 + k];
@@ -352,9 +394,14 @@ int cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int 
   NMRF_REQUIRE(C % 128 == 0 && C <= 512, "cost_volume_topk: C=%d must be a multiple of 128 (<=512)", C);
   NMRF_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, "cost_volume_topk: cost_group=%d unsupported", G);
   NMRF_REQUIRE(D >= 1 && D <= 128 && K >= 1 && K <= D, "cost_volume_topk: D=%d K=%d unsupported", D, K);
+  {
+    const int cpg4 = C / (4 * G);       // 16-byte channel chunks per correlation group: whole 32-chunk slabs, or a power of two below
+    NMRF_REQUIRE(cpg4 >= 1 && (cpg4 % 32 == 0 || (cpg4 < 32 && (cpg4 & (cpg4 - 1)) == 0)),
+                 "cost_volume_topk: C=%d with cost_group=%d is not supported (C / (4 G) = %d)", C, G, cpg4);
+  }
   NMRF_REQUIRE((reinterpret_cast<uintptr_t>(f1) & 15) == 0 && (reinterpret_cast<uintptr_t>(f2) & 15) == 0,
                "cost_volume_topk: feature maps must be 16-byte aligned (TMA bulk copies)");
-  const int DP = (D + 4 + 3 + 3) & ~3;
+  const int DP = cv_row_stride(D);
   const size_t featN = (size_t)(2 * TX + D - 1) * C, hidN = (size_t)TX * 24 * DP;
   const size_t smem = sizeof(float) * ((featN > hidN ? featN : hidN) + (size_t)TX * G * DP +
                                        (((size_t)TX * D + 3) & ~(size_t)3) + 8 * G * 5 + 8 + 16 * 8 * 5 + 16 + 16 * 5 + 4);

@@ -6,7 +6,9 @@ import torch
 class GraphedNMRF:
     """`runner(img1, img2)`: images may live on the host (pinned memory recommended) or on the device."""
 
-    def __init__(self, model, B, H, W, warmup=3):
+    def __init__(self, model, B, H, W, warmup=3, graph_full=True):
+        """graph_full=False: only the hot path is captured; the feature extractor runs eagerly.  For foreign encoders whose
+        forward cannot be captured (the reference's DeformNeck builds CPU tensors per call, adaptor_modules.py:27-34)."""
         assert model.device.type == "cuda"
         self.model = model
         dev = model.device
@@ -19,8 +21,12 @@ class GraphedNMRF:
                 model.forward_device(self.img1, self.img2)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        self.graph = None
+        if graph_full:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = model.forward_device(self.img1, self.img2)
+        else:
             self.out = model.forward_device(self.img1, self.img2)
         self.plan = model.plan_for(B, *self._feat_shape(model, B, H, W), H, W)
         self.disp_host = torch.empty(B, H, W, pin_memory=True)
@@ -38,7 +44,10 @@ class GraphedNMRF:
 
     def replay(self):
         """inputs already in self.img1/img2 (device-resident step)"""
-        self.graph.replay()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.out = self.model.forward_device(self.img1, self.img2)
         return self.out
 
     def replay_hot_path(self):
@@ -52,9 +61,12 @@ class GraphedNMRF:
         self._copy = torch.cuda.Stream(device=dev)
         self._stage_in = [(torch.empty_like(self.img1), torch.empty_like(self.img2)) for _ in range(2)]
         self._stage_out = [torch.empty_like(self.out["disp"]) for _ in range(2)]
-        self._host_out = [torch.empty(self.out["disp"].shape, pin_memory=True) for _ in range(2)]
+        # THREE pinned result buffers: result i lands in buffer i % 3, so the buffer handed out for result i - 1 is not
+        # written again before result i + 2 is enqueued, i.e. before the consumer has asked for the next-but-one item
+        self._host_out = [torch.empty(self.out["disp"].shape, pin_memory=True) for _ in range(3)]
         ev = lambda: torch.cuda.Event()
         self._ev_h2d, self._ev_in_free, self._ev_done, self._ev_d2h = ([ev(), ev()] for _ in range(4))
+        self._ev_host = [ev() for _ in range(3)]
         self._seq = 0
         self._primed = False
 
@@ -67,7 +79,7 @@ class GraphedNMRF:
 
     def stream(self, pairs):
         """Generator over (img1, img2) HOST pairs (pinned memory): yields each pair's disparity as a pinned host tensor that stays
-        valid until the next-but-one result is produced.  The H2D copy of pair i+1 and the D2H copy of pair i-1 run on a copy
+        valid until the next-but-one result has been requested (three result buffers rotate).  The H2D copy of pair i+1 and the D2H copy of pair i-1 run on a copy
         stream while pair i computes (the graph itself is unchanged: staging buffers are copied device-to-device)."""
         if not hasattr(self, "_copy"):
             self._pipeline_init()
@@ -88,26 +100,28 @@ class GraphedNMRF:
             main.wait_event(self._ev_h2d[slot])
             self.img1.copy_(self._stage_in[slot][0]); self.img2.copy_(self._stage_in[slot][1])
             self._ev_in_free[slot].record(main)
-            self.graph.replay()
+            self.replay()
             main.wait_event(self._ev_d2h[slot])                      # the D2H that last read this output staging buffer is done
             self._stage_out[slot].copy_(self.out["disp"])
             self._ev_done[slot].record(main)
+            hs = self._seq % 3
             with torch.cuda.stream(self._copy):
                 self._copy.wait_event(self._ev_done[slot])
-                self._host_out[slot].copy_(self._stage_out[slot], non_blocking=True)
+                self._host_out[hs].copy_(self._stage_out[slot], non_blocking=True)
                 self._ev_d2h[slot].record(self._copy)
+                self._ev_host[hs].record(self._copy)
             if pending is not None:
-                self._ev_d2h[pending].synchronize()
+                self._ev_host[pending].synchronize()
                 yield self._host_out[pending]
-            pending = slot
+            pending = hs
             self._seq += 1
-        self._ev_d2h[pending].synchronize()
+        self._ev_host[pending].synchronize()
         yield self._host_out[pending]
 
     def __call__(self, img1, img2, to_host=False):
         self.img1.copy_(img1, non_blocking=True)
         self.img2.copy_(img2, non_blocking=True)
-        self.graph.replay()
+        self.replay()
         if to_host:
             self.disp_host.copy_(self.out["disp"], non_blocking=True)
             return self.disp_host

@@ -22,7 +22,7 @@ for name, rows, Kx, Ke, N, ln, act, r in [("qkv", 34560, 128, 32, 384, True, 0, 
     gam, bet = torch.ones(Kx, device=dev), torch.zeros(Kx, device=dev)
     R = torch.randn(rows, N, generator=g).to(dev) if r else None
     Y = torch.empty(rows, N, device=dev)
-    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, Wt=Wt, out=Y)
+    kw = dict(E=E, ln=(gam, bet) if ln else None, ln_stats=ops.row_stats(X) if ln else None, bias=b, R=R, act=act, Wt=Wt, out=Y)
     for _ in range(3):
         ops.token_gemm(X, W, **kw)
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

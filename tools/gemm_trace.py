@@ -20,7 +20,7 @@ for name, rows, Kx, Ke, N, ln, act, res in [("fc2", 34560, 512, 0, 128, False, 0
     b = torch.randn(N, generator=g).to(dev)
     gam, bet = torch.ones(Kx, device=dev), torch.zeros(Kx, device=dev)
     R = torch.randn(rows, N, generator=g).to(dev) if res else None
-    kw = dict(E=E, ln=(gam, bet) if ln else None, bias=b, R=R, act=act, Wt=Wt)
+    kw = dict(E=E, ln=(gam, bet) if ln else None, ln_stats=ops.row_stats(X) if ln else None, bias=b, R=R, act=act, Wt=Wt)
     for _ in range(3):
         ops.token_gemm(X, W, **kw)
     tr = torch.zeros(4096, dtype=torch.int64, device=dev)

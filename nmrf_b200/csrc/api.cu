@@ -39,6 +39,8 @@ int check_launch(const char* what) {
 
 int token_gemm_simt(const nmrf_gemm_args& a, cudaStream_t stream);
 int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream);
+int token_gemm_ra(const nmrf_gemm_args& a, cudaStream_t stream);
+bool token_gemm_ra_supported(const nmrf_gemm_args& a);
 int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream);
 int row_stats(const float* X, int ldx, int rows, float* stats, cudaStream_t stream);
 int gemm6_set_trace(long long* dev_ptr);
@@ -110,6 +112,10 @@ int nmrf_token_gemm(const nmrf_gemm_args* a, void* stream) {
   NMRF_REQUIRE((a->Wt_hi == nullptr) == (a->Wt_lo == nullptr), "token_gemm: Wt_hi and Wt_lo go together");
   if (a->Wt_hi) {
     NMRF_REQUIRE(a->N % 16 == 0 && a->N <= 512, "token_gemm(tc): N=%d must be a multiple of 16, <= 512", a->N);
+    // K <= 192 (every nn.Linear of the hot path): A resident in tensor memory for the whole row block (gemm_ra.cu); longer
+    // contractions stream A per 128-column tile (gemm_tc6.cu).  NMRF_B200_GEMM_RA=0 (development A/B) forces the latter.
+    static const bool ra = [] { const char* e = getenv("NMRF_B200_GEMM_RA"); return !(e && e[0] == '0'); }();
+    if (ra && token_gemm_ra_supported(*a)) return token_gemm_ra(*a, ST(stream));
     return token_gemm_tc6(*a, ST(stream));
   }
   return token_gemm_simt(*a, ST(stream));

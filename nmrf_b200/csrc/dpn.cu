@@ -116,8 +116,8 @@ __device__ __forceinline__ void corr_pixel(const float* __restrict__ s_f1, const
 //           the CTA, serially over D).
 //   smem: f1 [TX][C], f2 [TX+D-1][C]  (dead after A1, re-used for h1 [TX][8][DP], h2 [TX][16][DP]), cv [TX][G][DP] (conv
 //         input, zero halos), logits [TX][D], conv weights: 70 KB at C = 256, D = 24
-__global__ void __launch_bounds__(CV_THREADS)
-cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ f2,
+__global__ void __launch_bounds__(CV_THREADS, 3)
+cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int ntiles,
                         int h, int w, int C, int G, int D, int K, float eps,
                         nmrf_seed_weights wt,
                         float* __restrict__ cost_volume, float* __restrict__ prob_out,
@@ -137,11 +137,6 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int tiles_x = (w + TX - 1) / TX;
-  const int tile = blockIdx.x % tiles_x;
-  const int by = blockIdx.x / tiles_x;       // b*h + y
-  const int x0 = tile * TX;
-  const int ntx = min(TX, w - x0);           // pixels of this tile inside the row
-  const size_t row_base = (size_t)by * w;    // pixel index of (b,y,0)
 
   // ---- stage: TMA bulk copies of the two feature tiles (one elected thread), weights by everybody meanwhile ---------------
   const uint32_t bar_a = cv_smem_u32(&bar);
@@ -150,15 +145,19 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0) {
-    const int xs = max(x0 - (D - 1), 0);                        // first f2 pixel that exists
-    const uint32_t bytes1 = (uint32_t)ntx * C * 4, bytes2 = (uint32_t)(x0 + ntx - xs) * C * 4;
+  // tile t -> TX pixels of row b*h + y; issued by thread 0 as soon as the staging area of the previous tile is dead
+  auto issue_tile = [&](int t) {
+    const int x0_ = (t % tiles_x) * TX, ntx_ = min(TX, w - x0_);
+    const size_t rb = (size_t)(t / tiles_x) * w;
+    const int xs = max(x0_ - (D - 1), 0);                       // first f2 pixel that exists
+    const uint32_t bytes1 = (uint32_t)ntx_ * C * 4, bytes2 = (uint32_t)(x0_ + ntx_ - xs) * C * 4;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes1 + bytes2) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(cv_smem_u32(s_f1)), "l"(f1 + (row_base + x0) * C), "r"(bytes1), "r"(bar_a) : "memory");
+                 ::"r"(cv_smem_u32(s_f1)), "l"(f1 + (rb + x0_) * C), "r"(bytes1), "r"(bar_a) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(cv_smem_u32(s_f2 + (size_t)(xs - (x0 - (D - 1))) * C)), "l"(f2 + (row_base + xs) * C), "r"(bytes2), "r"(bar_a) : "memory");
-  }
+                 ::"r"(cv_smem_u32(s_f2 + (size_t)(xs - (x0_ - (D - 1))) * C)), "l"(f2 + (rb + xs) * C), "r"(bytes2), "r"(bar_a) : "memory");
+  };
+  if (tid == 0 && (int)blockIdx.x < ntiles) issue_tile(blockIdx.x);
   const int nw0 = 8 * G * 5, nw1 = 16 * 8 * 5, nw2 = 16 * 5;
   float* sw0 = s_w; float* sb0 = sw0 + nw0; float* sw1 = sb0 + 8; float* sb1 = sw1 + nw1;
   float* sw2 = sb1 + 16; float* sb2 = sw2 + nw2;
@@ -168,12 +167,22 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
   if (tid < 8) sb0[tid] = wt.b0[tid];
   if (tid < 16) sb1[tid] = wt.b1[tid];
   if (tid == 0) sb2[0] = wt.b2[0];
+
+  // persistent over tiles (grid = 3 CTAs per SM): no partial last wave (544 tiles on 444 slots cost two full rounds), the conv
+  // weights are staged once, and the next tile's TMA copies fly under this tile's softmax / NMS / top-K
+  int it = 0;
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+  const int tile = t % tiles_x;
+  const int by = t / tiles_x;                // b*h + y
+  const int x0 = tile * TX;
+  const int ntx = min(TX, w - x0);           // pixels of this tile inside the row
+  const size_t row_base = (size_t)by * w;    // pixel index of (b,y,0)
   for (int i = tid; i < TX * G * DP; i += CV_THREADS) s_cv[i] = 0.f;   // conv halos (and the columns of pixels past the row end)
   {                                                                   // wait for the tiles (every thread observes the barrier)
     uint32_t done = 0;
     while (!done)
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done) : "r"(bar_a) : "memory");
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done) : "r"(bar_a), "r"(it & 1) : "memory");
   }
   __syncthreads();
 
@@ -269,6 +278,8 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
       if (d0 + j < D) s_lg[px * D + d0 + j] = acc[j];
   }
   __syncthreads();
+  // h1 | h2 (aliasing the feature staging) are dead: the next tile's copies may land while this tile finishes
+  if (tid == 0 && t + (int)gridDim.x < ntiles) issue_tile(t + gridDim.x);
 
   // ---- softmax over D, 1-D NMS, top-K: warp = pixel, lane holds d = lane + 32 j (D <= 128) -----------------------------------
   for (int px = warp; px < ntx; px += CV_WARPS) {
@@ -334,6 +345,7 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
         if (lane + 32 * j == bi) nv[j] = -INFINITY;
     }
   }
+  }   // tile loop (the next iteration's first __syncthreads orders this tile's reads of s_lg before its rewrite)
 }
 
 // A3/A4 gather: one warp per token.
@@ -408,9 +420,13 @@ int cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int 
   NMRF_REQUIRE(smem <= 227 * 1024, "cost_volume_topk: C=%d D=%d needs %zu B of shared memory", C, D, smem);
   static PerDevice configured;
   ensure_dynamic_smem(cost_volume_topk_kernel, (int)smem, configured);
-  const int tiles_x = (w + TX - 1) / TX;
-  cost_volume_topk_kernel<<<B * h * tiles_x, CV_THREADS, smem, stream>>>(f1, f2, h, w, C, G, D, K, eps, *wt,
-                                                                       cost_volume, prob, seeds);
+  const int tiles_x = (w + TX - 1) / TX, ntiles = B * h * tiles_x;
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 8) per_sm = 8;
+  const int grid = ntiles < per_sm * nmrf::num_sms() ? ntiles : per_sm * nmrf::num_sms();
+  cost_volume_topk_kernel<<<grid, CV_THREADS, smem, stream>>>(f1, f2, ntiles, h, w, C, G, D, K, eps, *wt,
+                                                             cost_volume, prob, seeds);
   count_launch();
   return check_launch("cost_volume_topk");
 }

@@ -186,6 +186,7 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
     uint32_t u = 0, grp = 0;
     int it = 0;
     for (int t = blockIdx.x; t < n_rb; t += tstep, ++it) {
+      uint32_t seen = 0;      // k-blocks of A this issuer has already waited for in this row block
       for (int c = 0; c < nch; ++c) {
         const uint32_t idesc = make_idesc(min(RA_BN, a.N - c * RA_BN));
         for (int kb = 0; kb < nkb; ++kb, ++u) {
@@ -194,7 +195,9 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
           const bool first = kb % G == 0, last = (kb % G == G - 1) || kb == nkb - 1;
           if ((grp & 1u) != me) { if (last) ++grp; continue; }
           if (first && grp >= (uint32_t)S) mbar_wait_warp(&sm.acc_empty[st], ((grp / S) - 1) & 1);   // the epilogue has read group - S
-          if (c == 0) mbar_wait_warp(&sm.a_full[kb], it & 1);                                        // A(kb) of this row block is in TMEM
+          // A(kb) of this row block is in TMEM.  Each issuer checks every k-block once per row block: with an odd number of
+          // groups per chunk the k-blocks an issuer meets in chunk 0 are not the ones it meets later.
+          if (!((seen >> kb) & 1u)) { mbar_wait_warp(&sm.a_full[kb], it & 1); seen |= 1u << kb; }
           mbar_wait_warp(&sm.full_b[slot], (u / RA_NB) & 1);                                        // the weight tile has landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (elect_one()) {

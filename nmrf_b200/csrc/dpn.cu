@@ -6,9 +6,15 @@
 namespace nmrf {
 namespace {
 
-constexpr int TX = 16;          // pixels of one image row per CTA
+#ifndef CV_TX
+#define CV_TX 16
+#endif
+constexpr int TX = CV_TX;       // pixels of one image row per CTA
 constexpr int CV_THREADS = 256;
 constexpr int CV_WARPS = CV_THREADS / 32;
+#ifndef CV_MINB
+#define CV_MINB 3
+#endif
 
 __device__ __forceinline__ uint32_t cv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -51,56 +57,32 @@ __device__ __forceinline__ void conv5_row(const float* __restrict__ in, int DP, 
   }
 }
 
-// A1 for one pixel: lane l owns the float4 channel chunks l + 32 j (j < NJ = C / 128): a warp's 16-byte loads cover 512
-// contiguous bytes (no bank conflicts; a blocked channel split reads with a 32-byte lane stride: 2-way).  Chunk l + 32 j
-// belongs to group (l + 32 j) / (C / (4 G)): the group sums are xor-shuffle reductions over LG = min(32, C / (4 G)) lanes.
-template <int NJ>
+// A1 for one pixel, one warp: lane = (group g = lane % G, dq = lane / G) computes whole dot products -- output (g, d) for
+// d = dq, dq + 32 / G, ... -- over the C / G channels of its group, 16 bytes of f1 and f2 per step.  No cross-lane reduction
+// (the first version of this round split the CHANNELS across lanes: three to four xor-shuffle stages per four disparities
+// plus index arithmetic for the scattered group sums were half of the kernel's 32 M instructions).  Lane r = lane % 8
+// starts at chunk r of its group and wraps: the eight lanes of a quarter-warp, whose rows / groups are whole multiples of
+// 128 B apart, read eight different bank groups.
 __device__ __forceinline__ void corr_pixel(const float* __restrict__ s_f1, const float* __restrict__ s_f2, float* __restrict__ s_cv,
                                            int px, int x, int C, int G, int D, int DP, int lane) {
-  const int cpg4 = C / (4 * G);                 // float4 chunks per group
-  const int LG = cpg4 < 32 ? cpg4 : 32;         // lanes that share a group within one 32-chunk slab
-  const float inv = 1.f / (float)(C / G);
-  float4 a[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; ++j) a[j] = *reinterpret_cast<const float4*>(s_f1 + px * C + (lane + 32 * j) * 4);
-  for (int d0 = 0; d0 < D; d0 += 4) {           // four disparities in flight
-    float s[4][NJ];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int d = min(d0 + e, D - 1);
-      const float* b = s_f2 + (size_t)(px + (D - 1) - d) * C + lane * 4;
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        const float4 vb = *reinterpret_cast<const float4*>(b + 128 * j);
-        s[e][j] = fmaf(a[j].x, vb.x, fmaf(a[j].y, vb.y, fmaf(a[j].z, vb.z, a[j].w * vb.w)));
-      }
+  const int lg = 31 - __clz(G);                 // G is a power of two
+  const int g = lane & (G - 1), dq = lane >> lg, dpw = 32 >> lg;
+  const int cg = C / G, nch4 = cg >> 2;         // channels / 16-byte chunks per group (>= 4: C % 128 == 0, G <= 8)
+  const int r = lane & (nch4 < 8 ? 3 : 7);
+  const float inv = 1.f / (float)cg;
+  const float4* a4 = reinterpret_cast<const float4*>(s_f1 + px * C + g * cg);
+  for (int d0 = 0; d0 < D; d0 += dpw) {
+    const int d = d0 + dq, dc = min(d, D - 1);
+    const float4* b4 = reinterpret_cast<const float4*>(s_f2 + (size_t)(px + (D - 1) - dc) * C + g * cg);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int i = r;
+#pragma unroll 4
+    for (int c = 0; c < nch4; ++c) {
+      const float4 va = a4[i], vb = b4[i];
+      s0 = fmaf(va.x, vb.x, s0); s1 = fmaf(va.y, vb.y, s1); s2 = fmaf(va.z, vb.z, s2); s3 = fmaf(va.w, vb.w, s3);
+      if (++i == nch4) i = 0;
     }
-    if (cpg4 >= 32) {                           // whole slabs belong to one group: add the slabs of a group first
-      const int spg = cpg4 / 32;                // slabs per group
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j)
-          if (j % spg != 0) s[e][j - j % spg] += s[e][j];
-    }
-    for (int o = LG >> 1; o > 0; o >>= 1) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e)
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) s[e][j] += __shfl_xor_sync(0xffffffffu, s[e][j], o);
-    }
-    if ((lane % LG) == 0) {
-#pragma unroll
-      for (int j = 0; j < NJ; ++j) {
-        if (cpg4 >= 32 && (j % (cpg4 / 32)) != 0) continue;
-        const int g = (lane + 32 * j) / cpg4;
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int d = d0 + e;
-          if (d < D) s_cv[(px * G + g) * DP + 4 + d] = (x >= d) ? s[e][j] * inv : 0.f;
-        }
-      }
-    }
+    if (d < D) s_cv[(px * G + g) * DP + 4 + d] = (x >= d) ? ((s0 + s1) + (s2 + s3)) * inv : 0.f;
   }
 }
 
@@ -108,15 +90,15 @@ __device__ __forceinline__ void corr_pixel(const float* __restrict__ s_f1, const
 // CTAs share an SM).  HBM sees every byte about once and nothing between the two feature maps and the outputs leaves the SM:
 //   stage   the f1 tile (TX pixels) and the f2 tile with its D-1 halo are each ONE contiguous run of an NHWC row: two TMA
 //           bulk copies (cp.async.bulk -> mbarrier), no per-thread loads;
-//   A1      group-wise correlation: warp = pixel, lane = interleaved 16-byte channel chunks (corr_pixel); f1 stays in registers
-//           over d, the G group sums come from xor-shuffles; the [TX,G,D] slab is assembled in shared memory and leaves as ONE
-//           contiguous run of cost_volume (16-byte coalesced stores), not as scattered 4-byte stores;
+//   A1      group-wise correlation: warp = pixel, lane = (group, disparity): whole dot products per lane, no shuffles
+//           (corr_pixel); the [TX,G,D] slab is assembled in shared memory and leaves as ONE contiguous run of cost_volume
+//           (16-byte coalesced stores), not as scattered 4-byte stores;
 //   A2      conv1d G->8->16->1: thread = (pixel, output channel), its 5 CI weights in registers, four d per step (conv5_row);
 //           softmax, 1-D NMS and top-K: WARP per pixel, lane = d, shuffles (the round-1 kernel ran them on 32 threads of
 //           the CTA, serially over D).
 //   smem: f1 [TX][C], f2 [TX+D-1][C]  (dead after A1, re-used for h1 [TX][8][DP], h2 [TX][16][DP]), cv [TX][G][DP] (conv
 //         input, zero halos), logits [TX][D], conv weights: 70 KB at C = 256, D = 24
-__global__ void __launch_bounds__(CV_THREADS, 3)
+__global__ void __launch_bounds__(CV_THREADS, CV_MINB)
 cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int ntiles,
                         int h, int w, int C, int G, int D, int K, float eps,
                         nmrf_seed_weights wt,
@@ -188,14 +170,7 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
 
   // ---- A1: group-wise correlation, warp = pixel (TX / 8 pixels per warp).  Pixels left of the image (x < d) read whatever the
   //      halo holds: their value is SELECTED to 0.
-  for (int px = warp; px < ntx; px += CV_WARPS) {
-    switch (C >> 7) {
-      case 1: corr_pixel<1>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
-      case 2: corr_pixel<2>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
-      case 3: corr_pixel<3>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
-      default: corr_pixel<4>(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane); break;
-    }
-  }
+  for (int px = warp; px < ntx; px += CV_WARPS) corr_pixel(s_f1, s_f2, s_cv, px, x0 + px, C, G, D, DP, lane);
   __syncthreads();
   // the tile's [ntx, G, D] slab is one contiguous run of cost_volume: coalesced 16-byte stores, consecutive threads ->
   // consecutive addresses (a (pixel, group) row of D floats sits at position 4 of its shared-memory row)
@@ -224,9 +199,10 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
 
   // ---- A2: conv1d G->8 (k5) + ReLU: thread = (pixel, output channel, half of the disparity chunks) ------------------------
   {
-    const int item = tid & (TX * 8 - 1), half = tid / (TX * 8);       // TX * 8 = 128 items, two threads each
+    constexpr int NPART = CV_THREADS / (TX * 8);                      // TX * 8 (pixel, channel) items, NPART threads each
+    const int item = tid & (TX * 8 - 1), part = tid / (TX * 8);
     const int px = item >> 3, co = item & 7;
-    const int cb = half ? (nch + 1) / 2 : 0, ce = half ? nch : (nch + 1) / 2;
+    const int cb = part * nch / NPART, ce = (part + 1) * nch / NPART;
     float wr[8][5];
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci)
@@ -243,15 +219,17 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
   }
   __syncthreads();
   if (D & 3) { zero_halo(s_h1, TX * 8, false); __syncthreads(); }      // a chunk wrote past D into the zero tail
-  // ---- conv1d 8->16 (k5) + ReLU: thread = (pixel, output channel), TX * 16 = all 256 threads -------------------------------
+  // ---- conv1d 8->16 (k5) + ReLU: thread = (pixel, output channel, part of the disparity chunks) -----------------------------
   {
-    const int px = tid >> 4, co = tid & 15;
+    constexpr int NPART = CV_THREADS / (TX * 16);
+    const int item = tid & (TX * 16 - 1), part = tid / (TX * 16);
+    const int px = item >> 4, co = item & 15;
     float wr[8][5];
 #pragma unroll
     for (int ci = 0; ci < 8; ++ci)
 #pragma unroll
       for (int k = 0; k < 5; ++k) wr[ci][k] = sw1[(co * 8 + ci) * 5 + k];
-    conv5_row<8>(s_h1 + px * 8 * DP, DP, 0, nch, wr, sb1[co], true, s_h2 + (px * 16 + co) * DP);
+    conv5_row<8>(s_h1 + px * 8 * DP, DP, part * nch / NPART, (part + 1) * nch / NPART, wr, sb1[co], true, s_h2 + (px * 16 + co) * DP);
   }
   __syncthreads();
   if (D & 3) { zero_halo(s_h2, TX * 16, false); __syncthreads(); }
@@ -333,12 +311,11 @@ cost_volume_topk_kernel(const float* __restrict__ f1, const float* __restrict__ 
         const int d = lane + 32 * j;
         if (d < D && nv[j] > best) { best = nv[j]; bi = d; }     // ascending d inside a lane: strict > keeps the first
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
+      // warp arg-max in two redux instructions: probabilities are >= 0, so their bit patterns order like the values
+      // (key 0 = nothing left in this lane); among the lanes holding the maximum the smallest index wins
+      const unsigned key = best >= 0.f ? __float_as_uint(best) + 1u : 0u;
+      const unsigned top = __reduce_max_sync(0xffffffffu, key);
+      bi = (int)__reduce_min_sync(0xffffffffu, key == top ? (unsigned)bi : 0xffffffffu);
       if (lane == 0) seeds[pix * K + k] = bi;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -406,11 +383,6 @@ int cost_volume_topk(const float* f1, const float* f2, int B, int h, int w, int 
   NMRF_REQUIRE(C % 128 == 0 && C <= 512, "cost_volume_topk: C=%d must be a multiple of 128 (<=512)", C);
   NMRF_REQUIRE(G == 1 || G == 2 || G == 4 || G == 8, "cost_volume_topk: cost_group=%d unsupported", G);
   NMRF_REQUIRE(D >= 1 && D <= 128 && K >= 1 && K <= D, "cost_volume_topk: D=%d K=%d unsupported", D, K);
-  {
-    const int cpg4 = C / (4 * G);       // 16-byte channel chunks per correlation group: whole 32-chunk slabs, or a power of two below
-    NMRF_REQUIRE(cpg4 >= 1 && (cpg4 % 32 == 0 || (cpg4 < 32 && (cpg4 & (cpg4 - 1)) == 0)),
-                 "cost_volume_topk: C=%d with cost_group=%d is not supported (C / (4 G) = %d)", C, G, cpg4);
-  }
   NMRF_REQUIRE((reinterpret_cast<uintptr_t>(f1) & 15) == 0 && (reinterpret_cast<uintptr_t>(f2) & 15) == 0,
                "cost_volume_topk: feature maps must be 16-byte aligned (TMA bulk copies)");
   const int DP = cv_row_stride(D);

@@ -31,6 +31,7 @@
 //               forward and flipped argmax / median decisions downstream.  (One stage per unit measured the same accuracy but
 //               let the MMA warp run only 3 units ahead of a tile's store phase: 84 instead of 35 us per launch.)
 //   waiting     all 32 lanes of a warp poll an mbarrier (tc_common.cuh: mbar_wait_warp): the warp stays converged.
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -77,7 +78,15 @@ struct ConvGeom {
   long long img_stride;      // floats between samples
   int Ho, Wo;                // output extent: rows = N * Ho * Wo
   int kw, stride, pad, cpb;  // kernel width, stride, padding, k-blocks (32 channels) per tap
+  int slab;                  // 3x3, stride 1, pad 1 over a dense NHWC tensor: the three taps of a kernel row share one raw slab
 };
+// SLAB mode.  These kernels run at the L2 -> SM ceiling (~30 B / cycle / SM measured, LTS cap ~42), and a 3x3 convolution
+// fetched tap by tap reads its input nine times.  With stride 1 / pad 1 the GEMM row index IS the flattened input pixel
+// index, so row r of a tile reads, for tap (ky, kx), flattened pixel p0 + r + (ky - 1) W + (kx - 1): the three kx taps of a
+// kernel row are the same 130 contiguous pixels shifted by one.  One slab [130 px x 32 ch] per (ky, channel block) serves
+// three units (k-block order ky, channel block, kx); what the flattening gets wrong (row / image borders) is exactly the
+// zero padding and is masked per row.  Two slab stages (17 KB each) live in the raw ring's 48 KB.
+constexpr int G6_SLAB_ROWS = G6_BM + 2, G6_SLAB_BYTES = 136 * 128;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -183,6 +192,24 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
     uint32_t f_ok = 0;
     int f_yx[4];               // CONV: (yo * stride - pad) << 16 | (xo * stride - pad) & 0xffff of the four rows
     int f_tap = 0, f_cb = 0;   // CONV: tap and channel block of the fetch cursor's k-block
+    const bool slab = CONV && cg.slab;
+    int f_s = 0;               // SLAB: (ky, channel block) of the fetch cursor
+    auto fetch_slab = [&](uint32_t stage) {
+      if (f_t < ntiles) {
+        const int ky = f_s / cg.cpb, cb = f_s - ky * cg.cpb;
+        const long long q0 = (long long)(f_t % n_rb) * G6_BM + (long long)(ky - 1) * cg.W - 1;
+        const uint32_t dst = smem_u32(sRaw(0)) + stage * G6_SLAB_BYTES;
+        for (int i = tid; i < G6_SLAB_ROWS * 8; i += G6_PROD) {
+          const int r = i >> 3;
+          const long long q = q0 + r;
+          const bool ok = q >= 0 && q < (long long)a.rows;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(r, f_c)),
+                       "l"(ok ? a.X + q * cg.pix_stride + cb * G6_BK + f_c * 4 : a.X), "r"(ok ? 16 : 0));
+        }
+        if (++f_s == 3 * cg.cpb) { f_s = 0; f_t += tstep; }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     auto fetch_tile = [&]() {
       const int row0 = (f_t % n_rb) * G6_BM;
       f_ok = 0;
@@ -206,7 +233,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
         }
       }
     };
-    if (f_t < ntiles) fetch_tile();
+    if (f_t < ntiles && !slab) fetch_tile();
     auto fetch_next = [&](uint32_t stage) {
       if (f_t < ntiles) {
         const uint32_t dst = smem_u32(sRaw(stage));
@@ -234,7 +261,9 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    fetch_next(0); fetch_next(1);
+    if (slab) fetch_slab(0);
+    else { fetch_next(0); fetch_next(1); }
+    uint32_t gslab = 0, tapmask = 0;   // SLAB: slabs consumed so far; bit ky * 3 + kx = this thread's row has that tap inside the image
     uint32_t unit = 0;         // == k-blocks produced so far by this CTA: ring stage unit % 4, A buffer unit & 1, B slot unit % 3
     int it = 0;
     for (int t = blockIdx.x; t < ntiles; t += tstep, ++it) {
@@ -255,22 +284,52 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
           mean = sm.mean[it % G6_STATS][a_row]; rstd = sm.rstd[it % G6_STATS][a_row];
         }
       }
+      if (slab) {
+        tapmask = 0;
+        if (row_ok) {
+          const int rem = (row0 + a_row) % (cg.H * cg.W);
+          const int yo = rem / cg.W, xo = rem - yo * cg.W;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx)
+              if ((unsigned)(yo + ky - 1) < (unsigned)cg.H && (unsigned)(xo + kx - 1) < (unsigned)cg.W) tapmask |= 1u << (ky * 3 + kx);
+        }
+      }
+      int s_kx = 0, s_sl = 0;          // SLAB: tap column and slab (ky * cpb + cb) of the unit
       for (int kb = 0; kb < nkb; ++kb, ++unit) {
         const int slot = unit % G6_NB;
         trace(tp, unit * 8 + 0);
-        // this k-block's raw tile has landed for every producer thread (own copies: wait_group; others': barrier)
-        asm volatile("cp.async.wait_group 1;" ::: "memory");
-        asm volatile("bar.sync %0, %1;" ::"r"(G6_RAW_BAR), "r"(G6_PROD) : "memory");
-        // the stage consumed one unit ago is free again (every producer is past its reads): re-arm it two k-blocks ahead
-        fetch_next((unit + 2) % G6_RAW);
+        const uint8_t* raw;
+        int rrow = a_row;
+        bool live = true;
+        if (slab) {
+          if (s_kx == 0) {
+            // the slab has landed for every producer thread, and everybody is past its reads of the previous one: prefetch the next
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync %0, %1;" ::"r"(G6_RAW_BAR), "r"(G6_PROD) : "memory");
+            fetch_slab((gslab + 1) & 1);
+          }
+          raw = sRaw(0) + (gslab & 1) * G6_SLAB_BYTES;
+          rrow = a_row + s_kx;
+          live = (tapmask >> ((s_sl / cg.cpb) * 3 + s_kx)) & 1u;
+          if (++s_kx == 3) { s_kx = 0; ++s_sl; ++gslab; }
+        } else {
+          // this k-block's raw tile has landed for every producer thread (own copies: wait_group; others': barrier)
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          asm volatile("bar.sync %0, %1;" ::"r"(G6_RAW_BAR), "r"(G6_PROD) : "memory");
+          // the stage consumed one unit ago is free again (every producer is past its reads): re-arm it two k-blocks ahead
+          fetch_next((unit + 2) % G6_RAW);
+          raw = sRaw(unit % G6_RAW);
+        }
         trace(tp2, 1024 + unit * 8 + 0);
-        const uint8_t* raw = sRaw(unit % G6_RAW);
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
           const int c = a_c0 + cc;
           const int kk = kb * G6_BK + c * 4;
-          float4 v = *reinterpret_cast<const float4*>(raw + swz(a_row, c));
+          float4 v = *reinterpret_cast<const float4*>(raw + swz(rrow, c));
+          if (CONV && !live) v = make_float4(0.f, 0.f, 0.f, 0.f);
           if (LN && row_ok && kk < a.Kx) {
             const float4 g = *reinterpret_cast<const float4*>(sm.gamma + kk);
             const float4 b = *reinterpret_cast<const float4*>(sm.beta + kk);
@@ -350,16 +409,25 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
       uint32_t unit = 0;
       for (int t = blockIdx.x; t < ntiles; t += tstep) {
         const int nchunk = t / n_rb;
+        // only the rows of the tile image this chunk multiplies (N - n_base < 128 for a last / only chunk, e.g. the 64-channel
+        // convolutions): a tile image is row-major, 128 B per output column, swizzled inside 8-row atoms -> a prefix of whole
+        // atoms is a valid smaller tile.  These kernels run at the L2 -> SM ceiling; the weight stream is 2/3 of their bytes.
+        const uint32_t tbytes = (uint32_t)((min(G6_BN, a.N - nchunk * G6_BN) + 7) & ~7) * 128u;
         for (int kb = 0; kb < nkb; ++kb, ++unit) {
           const int slot = unit % G6_NB;
           if (unit >= G6_NB) mbar_wait(&sm.done[slot], ((unit - G6_NB) / G6_NB) & 1);   // MMAs that read this slot are complete
-          const size_t toff = ((size_t)nchunk * nkb + kb) * (G6_TILE / 4);
+          int wkb = kb;
+          if (CONV && cg.slab) {                     // unit order (ky, channel block, kx) -> packed order (ky, kx, channel block)
+            const int sl = kb / 3, kx = kb - sl * 3, ky = sl / cg.cpb, cb = sl - ky * cg.cpb;
+            wkb = (ky * 3 + kx) * cg.cpb + cb;
+          }
+          const size_t toff = ((size_t)nchunk * nkb + wkb) * (G6_TILE / 4);
           const uint32_t bar = smem_u32(&sm.full_b[slot]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * G6_TILE) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * tbytes) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(sB_hi(slot))), "l"(a.Wt_hi + toff), "r"(G6_TILE), "r"(bar) : "memory");
+                       ::"r"(smem_u32(sB_hi(slot))), "l"(a.Wt_hi + toff), "r"(tbytes), "r"(bar) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(sB_lo(slot))), "l"(a.Wt_lo + toff), "r"(G6_TILE), "r"(bar) : "memory");
+                       ::"r"(smem_u32(sB_lo(slot))), "l"(a.Wt_lo + toff), "r"(tbytes), "r"(bar) : "memory");
         }
       }
     }
@@ -616,6 +684,10 @@ int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream) {
   ConvGeom g;
   g.H = c.H; g.W = c.W; g.pix_stride = c.pix_stride; g.row_stride = c.row_stride; g.img_stride = c.img_stride;
   g.Ho = Ho; g.Wo = Wo; g.kw = c.kw; g.stride = c.stride; g.pad = c.pad; g.cpb = c.Cin / 32;
+  g.slab = c.kh == 3 && c.kw == 3 && c.stride == 1 && c.pad == 1 && Ho == c.H && Wo == c.W &&
+           c.row_stride == (long long)c.W * c.pix_stride && c.img_stride == (long long)c.H * c.W * c.pix_stride;
+  static const bool slab_off = [] { const char* e = getenv("NMRF_B200_CONV_SLAB"); return e && e[0] == '0'; }();   // A/B switch
+  if (slab_off) g.slab = 0;
   const int num_sms = nmrf::num_sms();
   const int n_rb = (a.rows + G6_BM - 1) / G6_BM, n_nc = (a.N + G6_BN - 1) / G6_BN;
   const int ntiles = n_rb * n_nc;

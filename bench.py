@@ -18,8 +18,10 @@ baseline/_ref, with nmrf_b200.msda as its deformable-attention op), 1000x1500, D
            images and D2H of the disparity map of every step inside the timed region, overlapped with the neighbouring
            steps' compute (the number to hold against `--impl reference`).
   roofline: dominant kernel of the hot path (per-launch CUDA events, eager) against MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference: the oracle port of the reference's CPU forward (the Python reference
-           itself cannot travel to the GPU box) on all host cores.
+  cpu_baseline / --impl reference: the reference's CPU forward on the host cores -- the UNMODIFIED reference itself
+           (kind "reference") when its staged copy baseline/_ref is present (baseline/stage_reference.py; git-ignored, it
+           travels to the GPU box), else its oracle port (kind "port"); the thread count is calibrated, rank 0 only,
+           a bounded number of forwards.
 """
 import argparse
 import json
@@ -183,15 +185,49 @@ def time_cpu(fn, pairs, steps, warmup):
     return ts
 
 
+def reference_forward_fn(sd):
+    """The UNMODIFIED reference on the CPU through its own `NMRF.forward` (nmrf/models/NMRF.py:189-262), from the staged copy
+    baseline/_ref (baseline/stage_reference.py; git-ignored, travels with gpurun).  None when the copy is absent or does not
+    import here (then the oracle port is timed instead)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if WORKLOAD.get("swin") or not os.path.isdir(os.path.join(ref, "nmrf", "models")):
+        return None
+    try:
+        os.environ["NMRF_REFERENCE_ROOT"] = ref
+        from oracle import ref_shims
+        w = WORKLOAD
+        model = ref_shims.build_reference_model(max_disp=w["max_disp"], num_proposals=w["K"], num_prop_layers=w["L"][0],
+                                                num_infer_layers=w["L"][1], num_refine_layers=w["L"][2])
+        model.load_state_dict(sd)
+        model.eval()
+    except Exception as e:                       # noqa: BLE001  (report, fall back to the port)
+        print(f"[bench] staged reference not usable ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+        return None
+
+    def fn(a, b):
+        with torch.no_grad():
+            return model({"img1": a, "img2": b})["disp"]
+    return fn
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU forward (oracle port) on the host cores, rank 0 only."""
+    """--impl reference: the reference's CPU forward on the host cores, rank 0 only: the staged reference itself when
+    baseline/_ref is there, else its oracle port."""
     if rank != 0:
         return
     from nmrf_b200.synthetic import synthetic_pair
     w = WORKLOAD
+    if w.get("swin"):
+        print(json.dumps({"impl": "reference", "metric": METRIC, "config": {"workload": w["name"]},
+                          "unavailable": "the Swin-T encoder's CPU forward needs timm weights/ops that are not in this image"}))
+        return
     _, sd = build_model(None)
     pairs = [synthetic_pair(w["B"], w["H"], w["W"], w["max_disp"], i) for i in range(2)]
-    ts = time_cpu(oracle_forward_fn(sd), pairs, args.steps, max(args.warmup, 1))
+    fn = reference_forward_fn(sd)
+    kind = "reference" if fn is not None else "port"
+    what = ("the staged reference's NMRF.forward (baseline/_ref), torch CPU fp32" if fn is not None
+            else "oracle port of NMRF.forward, torch CPU fp32")
+    ts = time_cpu(fn or oracle_forward_fn(sd), pairs, args.steps, max(args.warmup, 1))
     total = sum(ts)
     val = w["B"] * len(ts) / total
     cores = torch.get_num_threads()
@@ -200,8 +236,8 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w["name"], "batch": w["B"], "parallelism": "cpu"},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port",
-                         "sample": f"{len(ts)} whole forwards of 1 pair (oracle port of NMRF.forward, torch CPU fp32)"},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(ts)} whole forwards of {w['B']} pair(s) ({what})"},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -352,9 +388,14 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         pairs = [synthetic_pair(B, H, W, w["max_disp"], i) for i in range(2)]
-        ts = time_cpu(oracle_forward_fn({k: v.cpu() for k, v in sd.items()}), pairs, 3, 1)
-        cpu = {"value": B * len(ts) / sum(ts), "unit": "pairs/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "3 whole forwards of 1 pair after 1 warm-up (oracle port of NMRF.forward, torch CPU fp32, all cores)"}
+        sd_cpu = {k: v.cpu() for k, v in sd.items()}
+        fn = reference_forward_fn(sd_cpu)
+        ts = time_cpu(fn or oracle_forward_fn(sd_cpu), pairs, 3, 1)
+        cpu = {"value": B * len(ts) / sum(ts), "unit": "pairs/s", "cores": torch.get_num_threads(),
+               "kind": "reference" if fn is not None else "port",
+               "sample": f"{len(ts)} whole forwards of {B} pair(s) after 1 warm-up (" +
+                         ("the staged reference's NMRF.forward, baseline/_ref" if fn is not None else "oracle port of NMRF.forward") +
+                         ", torch CPU fp32)"}
     if rank == 0:
         img_bytes = 2 * B * 3 * H * W * 4
         print(json.dumps({

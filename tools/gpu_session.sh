@@ -1,7 +1,9 @@
 set -x
-mkdir -p gpurun_out
-timeout 300 python tools/gemm_bench.py 20 2>&1 | tail -4
-NMRF_B200_LIB=nmrf_b200/libnmrf_b200_nohint.so timeout 300 python tools/gemm_bench.py 20 2>&1 | tail -4
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/s32_bench.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/s32_bench.log
-NMRF_B200_LIB=nmrf_b200/libnmrf_b200_nohint.so timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/s32_bench_nohint.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/s32_bench_nohint.log
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/s32_pytest.log 2>&1; tail -3 gpurun_out/s32_pytest.log
+mkdir -p gpurun_out/final
+O=gpurun_out/final
+nvidia-smi -L | head -8
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 --config c3 --steps 8 --warmup 3 > $O/bench_c3_4gpu.log 2>&1; tail -c 600 $O/bench_c3_4gpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 20 --warmup 5 > $O/bench_c1_4gpu.log 2>&1; tail -c 400 $O/bench_c1_4gpu.log
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 20 --warmup 5 > $O/bench_c1_2gpu.log 2>&1; tail -c 400 $O/bench_c1_2gpu.log
+timeout 900 python bench.py --config c3 --steps 8 --warmup 3 --no-cpu-baseline > $O/bench_c3_1gpu.log 2>&1; tail -c 300 $O/bench_c3_1gpu.log
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --impl reference --steps 1 --warmup 1 > $O/bench_ref_2gpu.log 2>&1; tail -c 300 $O/bench_ref_2gpu.log

@@ -40,12 +40,17 @@ __device__ __forceinline__ float rna_tf32_fast(float x) {
 // Error-compensated 3xTF32 operand split: x = hi + lo, hi = rn_tf32(x), lo = rn_tf32(x - hi).  x - hi is exact in fp32; the
 // tensor core reads only the upper 19 bits of an operand (it TRUNCATES), so an unrounded lo loses up to 2^-10 |lo| ~ 2^-21 |x|
 // per product -- four times the 2^-23 |x| of a rounded lo and enough to raise the rate of flipped argmax / median decisions
-// downstream (truncation split EPE 4.2e-3 px vs 7.6e-6 px for this one).  Two more integer ops per element.
+// downstream (truncation split EPE 4.2e-3 px vs 7.6e-6 px for this one).
+// Because of that truncation the rounding needs only its ADD: bits + 0x1000 carries into bit 13 exactly when the discarded
+// low bits are >= half an ulp, and the tensor core drops whatever remains below bit 13 itself (bit-identical results with
+// and without the mask: tools/dump_disp.py A/B; -DNMRF_LO_MASK builds the masked form).  One integer op per element.
 __device__ __forceinline__ float lo_tf32(float x, float hi) {
-#ifdef NMRF_LO_TRUNC
+#if defined(NMRF_LO_TRUNC)
   return x - hi;
-#else
+#elif defined(NMRF_LO_MASK)
   return rna_tf32_fast(x - hi);
+#else
+  return __uint_as_float(__float_as_uint(x - hi) + 0x1000u);
 #endif
 }
 

@@ -510,7 +510,10 @@ def test_instnorm_kernels(ops, N, H, W, C):
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k,stride,pad", [
     (2, 17, 23, 64, 64, 3, 1, 1), (1, 20, 31, 64, 96, 3, 2, 1), (2, 9, 12, 128, 384, 3, 1, 1), (1, 12, 16, 64, 96, 1, 2, 0),
-    (1, 6, 7, 256, 320, 3, 1, 1), (3, 5, 40, 96, 128, 1, 1, 0)])
+    (1, 6, 7, 256, 320, 3, 1, 1), (3, 5, 40, 96, 128, 1, 1, 0),
+    # slab mode (3x3, stride 1) edge cases: three channel blocks per tap, one-pixel-wide / one-pixel-high images (every
+    # horizontal / vertical neighbour is padding), and more row blocks than CTAs (slabs streamed across tiles of one CTA)
+    (1, 30, 50, 96, 96, 3, 1, 1), (2, 40, 1, 64, 64, 3, 1, 1), (1, 1, 300, 64, 80, 3, 1, 1), (1, 160, 130, 64, 64, 3, 1, 1)])
 def test_conv2d_against_float64(N, H, W, Cin, Cout, k, stride, pad):
     """nmrf_conv2d (implicit GEMM on tcgen05, 3xTF32, grouped accumulation) against torch's float64 convolution, next to the
     fp32 convolution of the reference arithmetic (torch CPU, ~2e-7 rms): at most 48 MMAs accumulate in place, which bounds the

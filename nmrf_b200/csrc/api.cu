@@ -46,6 +46,7 @@ int row_stats(const float* X, int ldx, int rows, float* stats, cudaStream_t stre
 int gemm6_set_trace(long long* dev_ptr);
 int mlp_chain(const nmrf_mlp_args& a, cudaStream_t stream);
 int mlp_set_trace(long long* dev_ptr);
+int ra_set_trace(long long* dev_ptr);
 int pack_weight_tiles(const float* w, int N, int K, float* hi, float* lo, cudaStream_t stream);
 int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t stream);
 int cost_volume_topk(const float*, const float*, int, int, int, int, int, int, int, float, const nmrf_seed_weights*,
@@ -147,6 +148,7 @@ int nmrf_pack_weight_tiles(const float* w, int N, int K, float* hi_tiles, float*
 int nmrf_debug_set_trace(void* dev_i64_4096) {
 #ifdef NMRF_TRACE
   mlp_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
+  ra_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
   return gemm6_set_trace(reinterpret_cast<long long*>(dev_i64_4096));
 #else
   if (dev_i64_4096 == nullptr) return NMRF_OK;

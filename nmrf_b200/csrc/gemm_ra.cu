@@ -50,6 +50,11 @@ __device__ __forceinline__ void ra_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+#ifdef NMRF_TRACE
+__device__ long long* g_trace_ra = nullptr;
+#endif
+#define ra_trace(cond, idx) NMRF_TRACE_STAMP((cond) ? tp : nullptr, idx)
+
 template <int ACT, bool LN>
 __global__ void __launch_bounds__(RA_BLOCK, 1)
 token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
@@ -61,6 +66,11 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
   float* stage_base = reinterpret_cast<float*>(base + RA_NB * RA_BTILE + RA_RAW * RA_RAWTILE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef NMRF_TRACE
+  // cycle stamps of CTA 0 (tools/ra_trace.py): producer thread 0 [0,256), MMA issuers [256,768) / [768,1280), TMA lane [1280,1536),
+  // epilogue warp 0 lane 0 [1536,2048)
+  long long* const tp = blockIdx.x == 0 && lane == 0 ? g_trace_ra : nullptr;
+#endif
   const int Ktot = a.Kx + a.Ke;
   const int nkb = (Ktot + RA_BK - 1) / RA_BK;               // <= RA_MAXKB (host check)
   const int nch = (a.N + RA_BN - 1) / RA_BN;                // 64-column chunks of the output
@@ -148,9 +158,11 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
         mean = st.x; rstd = st.y;
       }
       for (int kb = 0; kb < nkb; ++kb, ++unit) {
+        ra_trace(warp == 0 && unit < 64, unit * 4 + 0);
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(RA_RAW_BAR), "r"(RA_PROD) : "memory");
         fetch_next((unit + 2) % RA_RAW);
+        ra_trace(warp == 0 && unit < 64, unit * 4 + 1);
         const uint8_t* raw = sRaw(unit % RA_RAW);
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -174,6 +186,7 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
         }
         // A is single-buffered over row blocks: every MMA of the previous row block must be complete before its columns
         // are overwritten (the raw loads and the split above already ran under those MMAs)
+        ra_trace(warp == 0 && unit < 64, unit * 4 + 2);
         if (kb == 0 && it > 0) mbar_wait_warp(&sm.a_free, (it - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t ta = tmem + a_lane + (uint32_t)(kb * 64 + a_c0 * 4);
@@ -183,6 +196,7 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) ra_arrive(&sm.a_full[kb]);
+        ra_trace(warp == 0 && unit < 64, unit * 4 + 3);
       }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -203,12 +217,15 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
           const int st = grp % S;
           const bool first = kb % G == 0, last = (kb % G == G - 1) || kb == nkb - 1;
           if ((grp & 1u) != me) { if (last) ++grp; continue; }
+          ra_trace(u < 128, 256 + me * 512 + u * 4 + 0);
           if (first && grp >= (uint32_t)S) mbar_wait_warp(&sm.acc_empty[st], ((grp / S) - 1) & 1);   // the epilogue has read group - S
           // A(kb) of this row block is in TMEM.  Each issuer checks every k-block once per row block: with an odd number of
           // groups per chunk the k-blocks an issuer meets in chunk 0 are not the ones it meets later.
           if (!((seen >> kb) & 1u)) { mbar_wait_warp(&sm.a_full[kb], it & 1); seen |= 1u << kb; }
+          ra_trace(u < 128, 256 + me * 512 + u * 4 + 1);
           mbar_wait_warp(&sm.full_b[slot], (u / RA_NB) & 1);                                        // the weight tile has landed
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          ra_trace(u < 128, 256 + me * 512 + u * 4 + 2);
           if (elect_one()) {
             const uint32_t bslot = smem_u32(sB(slot));
             const uint64_t dBh = make_desc(bslot), dBl = make_desc(bslot + RA_BTILE / 2);
@@ -225,6 +242,7 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
             if (last) umma_commit(&sm.acc_full[st]);
           }
           __syncwarp();
+          ra_trace(u < 128, 256 + me * 512 + u * 4 + 3);
           if (last) ++grp;
         }
       }
@@ -240,7 +258,9 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
           const int c = chunk_of(ci);
           for (int kb = 0; kb < nkb; ++kb, ++u) {
             const int slot = u % RA_NB;
+            ra_trace(u < 128, 1280 + u * 2 + 0);
             if (u >= RA_NB) mbar_wait(&sm.done_b[slot], ((u - RA_NB) / RA_NB) & 1);
+            ra_trace(u < 128, 1280 + u * 2 + 1);
             // tile image (n-chunk c / 2, k-block kb): 128 rows x 128 B; rows 64 (c & 1) .. + 63 are 8 contiguous KB of it
             const size_t toff = ((size_t)(c >> 1) * nkb + kb) * 4096 + (size_t)(c & 1) * 2048;
             const uint32_t bar = smem_u32(&sm.full_b[slot]);
@@ -270,7 +290,9 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
         float acc[32];
         for (int gi = 0; gi < ngrp; ++gi, ++grp) {
           const int st = grp % S;
+          ra_trace(e == 0 && grp < 128, 1536 + grp * 4 + 0);
           mbar_wait_warp(&sm.acc_full[st], (grp / S) & 1, 32);
+          ra_trace(e == 0 && grp < 128, 1536 + grp * 4 + 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (mine) {
 #pragma unroll
@@ -288,6 +310,7 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
           }
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           ra_arrive(&sm.acc_empty[st]);
+          ra_trace(e == 0 && grp < 128, 1536 + grp * 4 + 2);
         }
         if (mine) {
 #pragma unroll
@@ -319,6 +342,7 @@ token_gemm_ra_kernel(const nmrf_gemm_args a, int n_rb) {
           }
           __syncwarp();
         }
+        ra_trace(e == 0 && grp - 1 < 128, 1536 + (grp - 1) * 4 + 3);
       }
     }
   }
@@ -338,6 +362,12 @@ void launch_ra(const nmrf_gemm_args& a, int n_rb, int grid, cudaStream_t stream)
 }
 
 }  // namespace
+
+#ifdef NMRF_TRACE
+int ra_set_trace(long long* dev_ptr) {
+  return cudaMemcpyToSymbol(g_trace_ra, &dev_ptr, sizeof(dev_ptr)) == cudaSuccess ? NMRF_OK : NMRF_ERR_CUDA;
+}
+#endif
 
 // K <= 192, tile images given, LayerNorm (if any) with handed-over statistics
 bool token_gemm_ra_supported(const nmrf_gemm_args& a) {

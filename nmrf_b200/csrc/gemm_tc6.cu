@@ -32,6 +32,8 @@
 //               let the MMA warp run only 3 units ahead of a tile's store phase: 84 instead of 35 us per launch.)
 //   waiting     all 32 lanes of a warp poll an mbarrier (tc_common.cuh: mbar_wait_warp): the warp stays converged.
 #include <cstdlib>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -59,6 +61,8 @@ struct G6Smem {
   uint64_t full_b[G6_NB];     // the slot's two weight tiles have landed (TMA bulk copy, expect_tx 32 KB)
   uint64_t acc_full[G6_ACC];  // accumulator stage holds a finished tile (tcgen05.commit)
   uint64_t acc_empty[G6_ACC]; // epilogue has drained the stage (256 arrivals)
+  uint64_t slab_full[2];      // SLAB mode: the raw slab has landed in the stage (TMA tensor copy, expect_tx 130 x 128 B)
+  uint64_t slab_free[2];      // SLAB mode: every producer warp is past its reads of the stage (8 arrivals)
   uint64_t stats_full[G6_STATS];          // LayerNorm statistics of a tile are in mean/rstd (8 arrivals: one per epilogue warp)
   uint32_t tmem_base;
   float mean[G6_STATS][G6_BM], rstd[G6_STATS][G6_BM];
@@ -85,7 +89,10 @@ struct ConvGeom {
 // index, so row r of a tile reads, for tap (ky, kx), flattened pixel p0 + r + (ky - 1) W + (kx - 1): the three kx taps of a
 // kernel row are the same 130 contiguous pixels shifted by one.  One slab [130 px x 32 ch] per (ky, channel block) serves
 // three units (k-block order ky, channel block, kx); what the flattening gets wrong (row / image borders) is exactly the
-// zero padding and is masked per row.  Two slab stages (17 KB each) live in the raw ring's 48 KB.
+// zero padding and is masked per row.  Two slab stages (17 KB each) live in the raw ring's 48 KB.  A slab is ONE TMA tensor
+// copy (2-D tensor map over [pixels, channels], box 130 x 32, hardware 128-byte swizzle = swz(), rows outside the tensor
+// zero-filled) issued by a lane of the TMA warp: the producers' own cp.async fetch -- address arithmetic, wait_group and a
+// 256-thread barrier per unit -- measured 15-20 % of a 3x3 convolution (tools/conv_bench.py with the fetch compiled out).
 constexpr int G6_SLAB_ROWS = G6_BM + 2, G6_SLAB_BYTES = 136 * 128;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -138,7 +145,7 @@ __device__ __noinline__ void tile_stats6(const float* __restrict__ X, int ldx, i
 // 96 registers per thread, which __launch_bounds__ makes ptxas respect (112 "fits" 65 536 / 576 but fails to launch)
 template <int ACT, bool LN, bool CONV>
 __global__ void __launch_bounds__(G6_BLOCK, 1)
-token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom cg) {
+token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom cg, const __grid_constant__ CUtensorMap amap) {
   extern __shared__ __align__(1024) uint8_t dsm[];
   __shared__ G6Smem sm;
   uint8_t* base = reinterpret_cast<uint8_t*>(((uintptr_t)dsm + 1023) & ~(uintptr_t)1023);
@@ -168,6 +175,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
     for (int i = 0; i < G6_NB; ++i) { mbar_init(&sm.done[i], 1); mbar_init(&sm.full_b[i], 1); }
     for (int i = 0; i < G6_ACC; ++i) { mbar_init(&sm.acc_full[i], 1); mbar_init(&sm.acc_empty[i], G6_EPI_WARPS * 32); }
     for (int i = 0; i < G6_STATS; ++i) mbar_init(&sm.stats_full[i], G6_EPI_WARPS);
+    for (int i = 0; i < 2; ++i) { mbar_init(&sm.slab_full[i], 1); mbar_init(&sm.slab_free[i], G6_PROD / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (LN && tid < 128) { sm.gamma[tid] = a.ln_gamma[tid]; sm.beta[tid] = a.ln_beta[tid]; }
@@ -193,23 +201,6 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
     int f_yx[4];               // CONV: (yo * stride - pad) << 16 | (xo * stride - pad) & 0xffff of the four rows
     int f_tap = 0, f_cb = 0;   // CONV: tap and channel block of the fetch cursor's k-block
     const bool slab = CONV && cg.slab;
-    int f_s = 0;               // SLAB: (ky, channel block) of the fetch cursor
-    auto fetch_slab = [&](uint32_t stage) {
-      if (f_t < ntiles) {
-        const int ky = f_s / cg.cpb, cb = f_s - ky * cg.cpb;
-        const long long q0 = (long long)(f_t % n_rb) * G6_BM + (long long)(ky - 1) * cg.W - 1;
-        const uint32_t dst = smem_u32(sRaw(0)) + stage * G6_SLAB_BYTES;
-        for (int i = tid; i < G6_SLAB_ROWS * 8; i += G6_PROD) {
-          const int r = i >> 3;
-          const long long q = q0 + r;
-          const bool ok = q >= 0 && q < (long long)a.rows;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + swz(r, f_c)),
-                       "l"(ok ? a.X + q * cg.pix_stride + cb * G6_BK + f_c * 4 : a.X), "r"(ok ? 16 : 0));
-        }
-        if (++f_s == 3 * cg.cpb) { f_s = 0; f_t += tstep; }
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    };
     auto fetch_tile = [&]() {
       const int row0 = (f_t % n_rb) * G6_BM;
       f_ok = 0;
@@ -261,8 +252,7 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    if (slab) fetch_slab(0);
-    else { fetch_next(0); fetch_next(1); }
+    if (!slab) { fetch_next(0); fetch_next(1); }
     uint32_t gslab = 0, tapmask = 0;   // SLAB: slabs consumed so far; bit ky * 3 + kx = this thread's row has that tap inside the image
     uint32_t unit = 0;         // == k-blocks produced so far by this CTA: ring stage unit % 4, A buffer unit & 1, B slot unit % 3
     int it = 0;
@@ -296,24 +286,20 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
               if ((unsigned)(yo + ky - 1) < (unsigned)cg.H && (unsigned)(xo + kx - 1) < (unsigned)cg.W) tapmask |= 1u << (ky * 3 + kx);
         }
       }
-      int s_kx = 0, s_sl = 0;          // SLAB: tap column and slab (ky * cpb + cb) of the unit
+      int s_kx = 0, s_cb = 0, s_ky = 0;   // SLAB: tap column, channel block and kernel row of the unit
       for (int kb = 0; kb < nkb; ++kb, ++unit) {
         const int slot = unit % G6_NB;
         trace(tp, unit * 8 + 0);
         const uint8_t* raw;
         int rrow = a_row;
         bool live = true;
+        bool slab_done = false;        // SLAB: this unit is the last reader of its slab
         if (slab) {
-          if (s_kx == 0) {
-            // the slab has landed for every producer thread, and everybody is past its reads of the previous one: prefetch the next
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            asm volatile("bar.sync %0, %1;" ::"r"(G6_RAW_BAR), "r"(G6_PROD) : "memory");
-            fetch_slab((gslab + 1) & 1);
-          }
+          if (s_kx == 0) mbar_wait_warp(&sm.slab_full[gslab & 1], (gslab >> 1) & 1);   // the slab of this kernel row has landed (TMA)
           raw = sRaw(0) + (gslab & 1) * G6_SLAB_BYTES;
           rrow = a_row + s_kx;
-          live = (tapmask >> ((s_sl / cg.cpb) * 3 + s_kx)) & 1u;
-          if (++s_kx == 3) { s_kx = 0; ++s_sl; ++gslab; }
+          live = (tapmask >> (s_ky * 3 + s_kx)) & 1u;
+          slab_done = s_kx == 2;
         } else {
           // this k-block's raw tile has landed for every producer thread (own copies: wait_group; others': barrier)
           asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -342,6 +328,16 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
             const float h = rna_tf32_fast(vv[j]);
             hi[cc * 4 + j] = __float_as_uint(h);
             lo[cc * 4 + j] = __float_as_uint(lo_tf32(vv[j], h));
+          }
+        }
+        if (slab) {
+          if (slab_done) {               // the slab's three taps are in registers: hand the stage back to the TMA lane
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.slab_free[gslab & 1]);
+            ++gslab; s_kx = 0;
+            if (++s_cb == cg.cpb) { s_cb = 0; ++s_ky; }
+          } else {
+            ++s_kx;
           }
         }
         trace(tp2, 1024 + unit * 8 + 1);
@@ -405,7 +401,24 @@ token_gemm_tc6_kernel(const nmrf_gemm_args a, int n_rb, int n_nc, const ConvGeom
     }
   } else if (warp == G6_TMA_WARP) {
     // =============================================== weight tiles (TMA) ===============================================
-    if (elect_one()) {
+    if (lane == 1 && CONV && cg.slab) {
+      // raw slabs of the A operand: slab gs -> stage gs & 1, one ahead of the producers (they free a stage after its third tap)
+      uint32_t gs = 0;
+      const uint32_t dst0 = smem_u32(sRaw(0));
+      for (int t = blockIdx.x; t < ntiles; t += tstep) {
+        const int row0 = (t % n_rb) * G6_BM;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int cb = 0; cb < cg.cpb; ++cb, ++gs) {
+            const uint32_t stage = gs & 1u;
+            if (gs >= 2) mbar_wait(&sm.slab_free[stage], ((gs >> 1) - 1) & 1);
+            const uint32_t bar = smem_u32(&sm.slab_full[stage]);
+            const int c0 = cb * G6_BK, c1 = row0 + (ky - 1) * cg.W - 1;      // (channel, flattened pixel) of the box origin
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(G6_SLAB_ROWS * 128) : "memory");
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst0 + stage * G6_SLAB_BYTES), "l"(reinterpret_cast<uint64_t>(&amap)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+          }
+      }
+    } else if (lane == 0) {
       uint32_t unit = 0;
       for (int t = blockIdx.x; t < ntiles; t += tstep) {
         const int nchunk = t / n_rb;
@@ -596,10 +609,28 @@ int split_tf32(const float* w, float* hi, float* lo, long long n, cudaStream_t s
 
 namespace {
 template <int ACT, bool LN, bool CONV = false>
-void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t stream, const ConvGeom& cg = ConvGeom()) {
+void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t stream, const ConvGeom& cg = ConvGeom(),
+             const CUtensorMap& amap = CUtensorMap()) {
   static PerDevice configured;        // per instantiation and device
   ensure_dynamic_smem(token_gemm_tc6_kernel<ACT, LN, CONV>, G6_DYN, configured);
-  token_gemm_tc6_kernel<ACT, LN, CONV><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc, cg);
+  token_gemm_tc6_kernel<ACT, LN, CONV><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc, cg, amap);
+}
+
+// 2-D tensor map over the NHWC activation seen as [pixels, channels] fp32 (pixel stride pix_stride floats): box = one slab
+bool encode_slab_map(const nmrf_conv_args& c, long long pixels, CUtensorMap* map) {
+  static const PFN_cuTensorMapEncodeTiled encode = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+  }();
+  if (!encode) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)c.Cin, (cuuint64_t)pixels};
+  const cuuint64_t gstr[1] = {(cuuint64_t)c.pix_stride * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)G6_BK, (cuuint32_t)G6_SLAB_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(c.X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 }  // namespace
 
@@ -688,10 +719,12 @@ int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream) {
            c.row_stride == (long long)c.W * c.pix_stride && c.img_stride == (long long)c.H * c.W * c.pix_stride;
   static const bool slab_off = [] { const char* e = getenv("NMRF_B200_CONV_SLAB"); return e && e[0] == '0'; }();   // A/B switch
   if (slab_off) g.slab = 0;
+  CUtensorMap amap = {};
+  if (g.slab && !encode_slab_map(c, (long long)c.N * c.H * c.W, &amap)) g.slab = 0;     // no driver entry point: tap-by-tap gather
   const int num_sms = nmrf::num_sms();
   const int n_rb = (a.rows + G6_BM - 1) / G6_BM, n_nc = (a.N + G6_BN - 1) / G6_BN;
   const int ntiles = n_rb * n_nc;
-  launch6<0, false, true>(a, n_rb, n_nc, ntiles < num_sms ? ntiles : num_sms, stream, g);
+  launch6<0, false, true>(a, n_rb, n_nc, ntiles < num_sms ? ntiles : num_sms, stream, g, amap);
   count_launch();
   return check_launch("conv2d");
 }

@@ -1,3 +1,3 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_stages.py -m gpu -q -k "conv2d" > gpurun_out/s35_pytest.log 2>&1; tail -15 gpurun_out/s35_pytest.log
+NMRF_B200_LIB=nmrf_b200/libnmrf_b200_trace.so timeout 300 python tools/ra_trace.py > gpurun_out/ra_trace.log 2>&1; tail -3 gpurun_out/ra_trace.log

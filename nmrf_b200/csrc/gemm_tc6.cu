@@ -32,9 +32,8 @@
 //               let the MMA warp run only 3 units ahead of a tile's store phase: 84 instead of 35 us per launch.)
 //   waiting     all 32 lanes of a warp poll an mbarrier (tc_common.cuh: mbar_wait_warp): the warp stays converged.
 #include <cstdlib>
-#include <cuda.h>
-#include <cudaTypedefs.h>
 #include "common.cuh"
+#include "tmap.cuh"
 #include "tc_common.cuh"
 
 namespace nmrf {
@@ -616,22 +615,6 @@ void launch6(const nmrf_gemm_args& a, int n_rb, int n_nc, int grid, cudaStream_t
   token_gemm_tc6_kernel<ACT, LN, CONV><<<grid, G6_BLOCK, G6_DYN, stream>>>(a, n_rb, n_nc, cg, amap);
 }
 
-// 2-D tensor map over the NHWC activation seen as [pixels, channels] fp32 (pixel stride pix_stride floats): box = one slab
-bool encode_slab_map(const nmrf_conv_args& c, long long pixels, CUtensorMap* map) {
-  static const PFN_cuTensorMapEncodeTiled encode = [] {
-    void* f = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
-    return reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
-  }();
-  if (!encode) return false;
-  const cuuint64_t gdim[2] = {(cuuint64_t)c.Cin, (cuuint64_t)pixels};
-  const cuuint64_t gstr[1] = {(cuuint64_t)c.pix_stride * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)G6_BK, (cuuint32_t)G6_SLAB_ROWS};
-  const cuuint32_t estr[2] = {1, 1};
-  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(c.X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 }  // namespace
 
 int token_gemm_tc6(const nmrf_gemm_args& a, cudaStream_t stream) {
@@ -720,7 +703,9 @@ int conv2d_tc6(const nmrf_conv_args& c, cudaStream_t stream) {
   static const bool slab_off = [] { const char* e = getenv("NMRF_B200_CONV_SLAB"); return e && e[0] == '0'; }();   // A/B switch
   if (slab_off) g.slab = 0;
   CUtensorMap amap = {};
-  if (g.slab && !encode_slab_map(c, (long long)c.N * c.H * c.W, &amap)) g.slab = 0;     // no driver entry point: tap-by-tap gather
+  // the NHWC activation seen as [pixels, channels] (pixel stride pix_stride floats); box = one slab.  No driver entry point:
+  // tap-by-tap gather
+  if (g.slab && !encode_tmap_2d(&amap, c.X, (long long)c.N * c.H * c.W, c.Cin, c.pix_stride, G6_SLAB_ROWS, G6_BK)) g.slab = 0;
   const int num_sms = nmrf::num_sms();
   const int n_rb = (a.rows + G6_BM - 1) / G6_BM, n_nc = (a.N + G6_BN - 1) / G6_BN;
   const int ntiles = n_rb * n_nc;

@@ -1,6 +1,5 @@
 set -x
-mkdir -p gpurun_out/final
-O=gpurun_out/final
-nvidia-smi -L | wc -l
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29521 bench.py --gpus 8 --config c4 --steps 8 --warmup 3 > $O/bench_c4_8gpu.log 2>&1; tail -c 500 $O/bench_c4_8gpu.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29522 bench.py --gpus 8 --steps 20 --warmup 5 > $O/bench_c1_8gpu.log 2>&1; tail -c 400 $O/bench_c1_8gpu.log
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_stages.py -m gpu -q -x -k "conv2d or encoder or instnorm" > gpurun_out/s46_pytest_a.log 2>&1; tail -8 gpurun_out/s46_pytest_a.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/s46_bench.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/s46_bench.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/s46_pytest.log 2>&1; tail -3 gpurun_out/s46_pytest.log

@@ -1,5 +1,9 @@
 set -x
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_stages.py -m gpu -q -x -k "conv2d or encoder or instnorm" > gpurun_out/s46_pytest_a.log 2>&1; tail -8 gpurun_out/s46_pytest_a.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/s46_bench.log 2>&1; grep -o '"ms_per_step": [0-9.]*' gpurun_out/s46_bench.log
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/s46_pytest.log 2>&1; tail -3 gpurun_out/s46_pytest.log
+mkdir -p gpurun_out/final
+O=gpurun_out/final
+timeout 900 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; tail -3 $O/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
+timeout 900 python bench.py > $O/bench_c1.log 2>&1; tail -c 300 $O/bench_c1.log
+timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_c1_reference.log 2>&1; tail -c 200 $O/bench_c1_reference.log
+for c in c1b c2 c4; do timeout 900 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_$c.log 2>&1; tail -c 150 $O/bench_$c.log; done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_torchrun1.log 2>&1; tail -c 150 $O/bench_torchrun1.log

@@ -3,7 +3,7 @@ import json
 import sys
 
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-out = [f"hot ms {round(d['ms_per_step'], 3)} full {round(d['full_forward']['ms_per_step'], 3)} e2e {round(d['e2e']['value'], 2)}"]
+out = [f"hot ms {round(d['hot_path']['ms_per_step'], 3)} full {round(d['ms_per_step'], 3)} e2e {round(d['e2e']['value'], 2)}"]
 for k, v in d["hot_path"]["kernels"].items():
     if v["ms"] > 0.1:
         out.append(f"   {k} {v['ms']} {v['launches']}")

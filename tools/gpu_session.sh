@@ -1,3 +1,4 @@
+# What a round-end check runs on the GPU box (gpurun -- 'bash tools/gpu_session.sh'); outputs under gpurun_out/final/
 set -x
 mkdir -p gpurun_out/final
 O=gpurun_out/final
@@ -6,4 +7,3 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>
 timeout 900 python bench.py > $O/bench_c1.log 2>&1; tail -c 300 $O/bench_c1.log
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_c1_reference.log 2>&1; tail -c 200 $O/bench_c1_reference.log
 for c in c1b c2 c4; do timeout 900 python bench.py --config $c --steps 10 --warmup 3 --no-cpu-baseline > $O/bench_$c.log 2>&1; tail -c 150 $O/bench_$c.log; done
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 1 --steps 5 --warmup 3 --no-cpu-baseline > $O/bench_torchrun1.log 2>&1; tail -c 150 $O/bench_torchrun1.log

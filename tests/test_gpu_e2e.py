@@ -160,6 +160,42 @@ def test_stage_chain_with_stress_weights():
         assert rel(x.reshape(-1, K, 128), taps[f"inference_layer{i}"]) <= 2e-4, f"inference layer {i}"
 
 
+def test_refinement_stage_chain_with_stress_weights():
+    """mirror of the test above for the 1/4-resolution refinement stack (K = 1, window 4, shift 2, no self-edge mask,
+    normalizer 3.14 / 128; reference NMP.py:828-900): the plan's conv-head maps + the ORACLE's disp_curr through the public ops"""
+    import nmrf_b200.ops as ops
+    from nmrf_b200.hotpath import center_pad
+    max_disp, K, L = 192, 4, (2, 2, 2)
+    model, sd = build_product_model(max_disp, K, L, 5, "stress")
+    model = model.cuda()
+    B, H, W = 1, 104, 184
+    img1, img2 = synthetic_pair(B, H, W, max_disp, index=4)
+    cfg = oracle_cfg(max_disp, K, L)
+    O.forward(sd, cfg, img1, img2)
+    taps = cfg.taps
+    model({"img1": img1, "img2": img2})
+    plan = next(iter(model._plans.values()))
+    rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-6))
+    h4, w4 = H // 4, W // 4
+    Hp, top = center_pad(h4, 4)
+    Wp, left = center_pad(w4, 4)
+    pw = model._packed
+    disp_curr = taps["disp_curr"].reshape(B * h4 * w4, 1).cuda().contiguous()
+    feat, enc = ops.warp_corr_embed(plan.cc4[0], plan.cc4[1], plan.gw4[0], plan.gw4[1], disp_curr, 1, Hp, Wp, top, left, 3.14 / 128)
+    S = pw.stacks["refinement"]
+    x = ops.token_gemm(ops.token_gemm(feat, S["ffn1_w"], bias=S["ffn1_b"], act=2), S["ffn2_w"], bias=S["ffn2_b"])
+    ops.zero_pad_rows(x, B, h4, w4, 1, Hp, Wp, top, left)
+    emb = x.reshape(B, Hp, Wp, 1, 128)[:, top:top + h4, left:left + w4].reshape(-1, 1, 128)
+    assert rel(emb, taps["refinement_embed"]) <= 1e-4
+    for i, wt in enumerate(S["layers"]):
+        qkv = ops.token_gemm(x, wt["qkv_w"], E=enc, ln=wt["n1"], bias=wt["qkv_b"])
+        att = ops.window_attention(qkv, wt["table"], B, Hp, Wp, 1, 4, 0 if i % 2 == 0 else 2, False)
+        x = ops.token_gemm(att, wt["proj_w"], bias=wt["proj_b"], R=x)
+        hid = ops.token_gemm(x, wt["fc1_w"], ln=wt["n2"], bias=wt["fc1_b"], act=2)
+        x = ops.token_gemm(hid, wt["fc2_w"], bias=wt["fc2_b"], R=x)
+        assert rel(x.reshape(-1, 1, 128), taps[f"refinement_layer{i}"]) <= 2e-4, f"refinement layer {i}"
+
+
 def test_full_size_properties():
     """540x960, D=24, K=4 (BASELINE config 1 geometry, 2 layers per stack to keep it quick):
     determinism, batch independence, and agreement with the oracle (~5 s of CPU)."""
